@@ -1,0 +1,134 @@
+/* sedb.h -- C ABI of libsedb.so: the B200-native hot path of ariel415el/SoundEventDetection-Pytorch.
+ *
+ * The reference is pure Python and has no FFI layer; the boundary it exposes for this path is the
+ * set of Python callables cited below (paths relative to the reference repository).  Each entry
+ * point here is what a binding for that callable would call.  Conventions:
+ *   - every function returns 0 on success and a non-zero code on failure; the message is available
+ *     from sedb_last_error() (thread-local).  Nothing throws or aborts across the boundary.
+ *   - "dev" pointers are CUDA device pointers on the device that was current when the context was
+ *     created; "host" pointers are ordinary (ideally pinned) host memory.
+ *   - the caller owns every input/output buffer; the context owns only constant tables and packed
+ *     weight copies.  Device entry points are asynchronous and stream-ordered on `stream`
+ *     (a cudaStream_t passed as void*; NULL = legacy default stream); they never synchronise.
+ *   - a context may be used from one host thread at a time; one context per GPU.
+ *   - there is no CPU fallback: without a CUDA device every compute entry point fails.
+ */
+#ifndef SEDB_H_
+#define SEDB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEDB_ABI_VERSION 1
+
+/* configuration the kernels are specialised for (dataset/common_config.py:2-8,
+ * dataset/spectogram/spectogram_configs.py:5-8) */
+#define SEDB_SAMPLE_RATE 48000
+#define SEDB_FRAME_SIZE 31680
+#define SEDB_HOP_SIZE 15840
+#define SEDB_NFFT 32768
+#define SEDB_NUM_BINS 16385
+#define SEDB_MEL_BINS 64
+#define SEDB_MEL_FMIN 20.0f
+#define SEDB_MEL_FMAX 24000.0f
+
+typedef struct sedb_ctx sedb_ctx_t;
+typedef struct sedb_cnn sedb_cnn_t;
+typedef struct sedb_m5 sedb_m5_t;
+
+/* ---- library / configuration ------------------------------------------------------------------ */
+int sedb_version(void);
+const char* sedb_last_error(void);
+/* 1 if the library was built with fp16 split operands (+ block scaling), 0 for bf16 split operands */
+int sedb_split_is_fp16(void);
+/* Refuses (non-zero) when the caller's dataset/spectogram/spectogram_configs.py constants differ from
+ * the compile-time specialisation above. */
+int sedb_check_config(int sample_rate, int frame_size, int hop_size, int nfft, int mel_bins, float fmin,
+                      float fmax);
+/* T = 1 + n_samples / hop  (librosa.stft(center=True) as called at dataset/spectogram/preprocess.py:25-33) */
+long long sedb_num_frames(long long n_samples);
+
+int sedb_create(sedb_ctx_t** out_ctx);
+int sedb_destroy(sedb_ctx_t* ctx);
+
+/* ---- log-mel feature extraction ---------------------------------------------------------------- */
+/* MEL_FILTER_BANK_MATRIX (dataset/spectogram/preprocess.py:13-18): writes the (16385, 64) float32
+ * row-major matrix the kernels use to host memory.  Host-only, no device needed. */
+int sedb_mel_filterbank(float* out_host);
+
+/* Fused multichannel_complex_to_log_mel(multichannel_stft(x)) (preprocess.py:21-45) for a batch of mono
+ * clips.  wave_dev: [n_clips, wave_stride] float32 (n_samples valid per clip, n_samples > 16384);
+ * norm_dev: NULL or mean[64] followed by std[64] (SpectogramDataset.transform, spectograms_dataset.py:104-105);
+ * out_dev: [n_clips, T, 64] float32. */
+int sedb_logmel_f32(sedb_ctx_t* ctx, const float* wave_dev, long long n_clips, long long n_samples,
+                    long long wave_stride, const float* norm_dev, float* out_dev, void* stream);
+
+/* multichannel_stft (preprocess.py:21-36): spec_dev: [n_clips, T, 16385] complex64 (interleaved re,im). */
+int sedb_stft_c64(sedb_ctx_t* ctx, const float* wave_dev, long long n_clips, long long n_samples,
+                  long long wave_stride, float* spec_dev, void* stream);
+
+/* multichannel_complex_to_log_mel (preprocess.py:39-45) on an existing complex64 spectrogram:
+ * spec_dev: [rows, 16385] complex64; out_dev: [rows, 64] float32. */
+int sedb_power_mel_db_f32(sedb_ctx_t* ctx, const float* spec_dev, long long rows, const float* norm_dev,
+                          float* out_dev, void* stream);
+
+/* Host-buffer variant of sedb_logmel_f32: copies clips host->device in chunks overlapped with compute on
+ * internal streams and copies the log-mel image back; synchronises before returning.  wave_host and
+ * out_host should be pinned for full PCIe bandwidth. */
+int sedb_logmel_host_f32(sedb_ctx_t* ctx, const float* wave_host, long long n_clips, long long n_samples,
+                         long long wave_stride, const float* norm_host, float* out_host);
+
+/* ---- spectrogram CNN: Cnn_AvgPooling (models/spectogram_models.py:163-205) ----------------------- */
+/* channels[i], pools[i]: model_config entries (spectogram_models.py:7, main.py:35); input channels = 1. */
+int sedb_cnn_create(sedb_ctx_t* ctx, const int* channels, const int* pools, int n_blocks, int classes_num,
+                    sedb_cnn_t** out);
+int sedb_cnn_destroy(sedb_cnn_t* cnn);
+/* tensors_dev: device float32 pointers in state_dict order per block:
+ *   conv1.weight, conv2.weight, bn1.{weight,bias,running_mean,running_var}, bn2.{weight,bias,running_mean,running_var}
+ * followed by event_fc.weight, event_fc.bias.  BatchNorm (eps 1e-5) is folded into per-channel scale/shift.
+ * Must be called again after the parameters change. */
+int sedb_cnn_load(sedb_cnn_t* cnn, const float* const* tensors_dev, int n_tensors, void* stream);
+/* frames produced for T input frames: ratio * floor-pooled(T)  (spectogram_models.py:185-202) */
+long long sedb_cnn_out_frames(const sedb_cnn_t* cnn, long long T);
+size_t sedb_cnn_workspace_bytes(const sedb_cnn_t* cnn, long long n_clips, long long T);
+/* x_dev: [n_clips, 1, T, 64] float32 log-mel; logits_dev / probs_dev (either may be NULL):
+ * [n_clips, out_frames, classes] float32 = forward() / logits() of the reference module. */
+int sedb_cnn_forward(sedb_cnn_t* cnn, const float* x_dev, long long n_clips, long long T, float* logits_dev,
+                     float* probs_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- waveform CNN: M5 (models/waveform_models.py:9-71) ------------------------------------------ */
+int sedb_m5_create(sedb_ctx_t* ctx, int classes_num, sedb_m5_t** out);
+int sedb_m5_destroy(sedb_m5_t* m5);
+/* tensors_dev in state_dict order: for each Conv1d+BatchNorm1d pair
+ *   conv.weight, conv.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var   (9 pairs)
+ * then fc.weight, fc.bias. */
+int sedb_m5_load(sedb_m5_t* m5, const float* const* tensors_dev, int n_tensors, void* stream);
+size_t sedb_m5_workspace_bytes(const sedb_m5_t* m5, long long n_frames);
+/* x_dev: [n_frames, 1, 31680] float32; logits_dev: [n_frames, classes] float32. */
+int sedb_m5_forward(sedb_m5_t* m5, const float* x_dev, long long n_frames, float* logits_dev,
+                    void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/* ---- end-to-end: waveform -> log-mel -> CNN -> frame probabilities -------------------------------- */
+/* infer.py:27-33 intent.  wave_host: [n_clips, wave_stride] float32 host; probs_host: [n_clips, out_frames,
+ * classes] float32 host.  H2D chunks, log-mel, CNN and the D2H of the probabilities are pipelined. */
+int sedb_sed_host_f32(sedb_ctx_t* ctx, sedb_cnn_t* cnn, const float* wave_host, long long n_clips,
+                      long long n_samples, long long wave_stride, const float* norm_host, float* probs_host);
+
+/* ---- diagnostics ---------------------------------------------------------------------------------- */
+/* One-CTA tcgen05 GEMM probe used by the GPU tests to pin the shared-memory descriptor conventions:
+ * D[128,N] = A[128,K] * B[K,N] with bf16-rounded operands.  a_dev/b_dev/d_dev are float32 row-major.
+ * a_major/b_major: 0 = K-major, 1 = MN-major canonical layout; pad: extra bytes added to the 8-row group
+ * stride; neg_b: set the B-negate bit. */
+int sedb_debug_umma_probe(const float* a_dev, const float* b_dev, float* d_dev, int N, int K, int a_major,
+                          int b_major, int pad, int neg_b, int swap_lbo_sbo, void* stream);
+/* Number of kernel launches issued through this library since load (bench.py's gpu_launches). */
+long long sedb_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEDB_H_ */

@@ -1,0 +1,145 @@
+// Host-side generation of the constant tables the kernels consume: split DFT matrices in the tcgen05
+// canonical shared-memory layout, and the Slaney mel filterbank of the reference
+// (librosa.filters.mel as called at dataset/spectogram/preprocess.py:13-18).
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+
+namespace sedb_host {
+
+constexpr double kPi = 3.14159265358979323846;
+
+inline uint16_t to_split_bits(float x, bool fp16) {
+    if (fp16) {
+        __half h = __float2half_rn(x);
+        uint16_t u;
+        std::memcpy(&u, &h, 2);
+        return u;
+    }
+    __nv_bfloat16 b = __float2bfloat16_rn(x);
+    uint16_t u;
+    std::memcpy(&u, &b, 2);
+    return u;
+}
+inline float from_split_bits(uint16_t u, bool fp16) {
+    if (fp16) {
+        __half h;
+        std::memcpy(&h, &u, 2);
+        return __half2float(h);
+    }
+    __nv_bfloat16 b;
+    std::memcpy(&b, &u, 2);
+    return __bfloat162float(b);
+}
+inline void split_hi_lo(double v, bool fp16, uint16_t& hi, uint16_t& lo) {
+    const float x = static_cast<float>(v);
+    hi = to_split_bits(x, fp16);
+    lo = to_split_bits(x - from_split_bits(hi, fp16), fp16);
+}
+
+// Stage-1 constants: 16 K-chunks x {cH, cL, sH, sL} x [128 rows k1][16 k = n1 - 16 c], K-major canonical
+// (byte = (k/8)*2048 + m*16 + (k%8)*2).  Row 0 of the sine block carries (-1)^n1, i.e. k1 = 128.
+inline std::vector<uint8_t> make_stage1_constants(bool fp16) {
+    std::vector<uint8_t> buf(16 * 4 * 4096);
+    for (int c = 0; c < 16; ++c)
+        for (int m = 0; m < 128; ++m)
+            for (int kk = 0; kk < 16; ++kk) {
+                const int n1 = 16 * c + kk;
+                const double ang = 2.0 * kPi * static_cast<double>((m * n1) % 256) / 256.0;
+                double cv = std::cos(ang), sv = -std::sin(ang);
+                if (m == 0) sv = (n1 & 1) ? -1.0 : 1.0;
+                uint16_t ch, cl, sh, sl;
+                split_hi_lo(cv, fp16, ch, cl);
+                split_hi_lo(sv, fp16, sh, sl);
+                const size_t off = static_cast<size_t>(c) * 16384 + (kk / 8) * 2048 + m * 16 + (kk % 8) * 2;
+                std::memcpy(&buf[off + 0 * 4096], &ch, 2);
+                std::memcpy(&buf[off + 1 * 4096], &cl, 2);
+                std::memcpy(&buf[off + 2 * 4096], &sh, 2);
+                std::memcpy(&buf[off + 3 * 4096], &sl, 2);
+            }
+    return buf;
+}
+
+// Stage-2 constants: {cH, cL, sH, sL} x [128 n = k2][128 k = n2], K-major canonical; c = cos, s = +sin of
+// 2 pi n2 k2 / 128 (exp(-i a) = c - i s).
+inline std::vector<uint8_t> make_stage2_constants(bool fp16) {
+    std::vector<uint8_t> buf(4 * 32768);
+    for (int n = 0; n < 128; ++n)
+        for (int k = 0; k < 128; ++k) {
+            const double ang = 2.0 * kPi * static_cast<double>((n * k) % 128) / 128.0;
+            uint16_t ch, cl, sh, sl;
+            split_hi_lo(std::cos(ang), fp16, ch, cl);
+            split_hi_lo(std::sin(ang), fp16, sh, sl);
+            const size_t off = static_cast<size_t>(k / 8) * 2048 + n * 16 + (k % 8) * 2;
+            std::memcpy(&buf[off + 0 * 32768], &ch, 2);
+            std::memcpy(&buf[off + 1 * 32768], &cl, 2);
+            std::memcpy(&buf[off + 2 * 32768], &sh, 2);
+            std::memcpy(&buf[off + 3 * 32768], &sl, 2);
+        }
+    return buf;
+}
+
+// ---- librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax, htk=False, norm='slaney') --------------------
+inline double hz_to_mel(double f) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = std::log(6.4) / 27.0;
+    return (f >= min_log_hz) ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+inline double mel_to_hz(double m) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;
+    const double logstep = std::log(6.4) / 27.0;
+    return (m >= min_log_mel) ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+
+// Returns the dense (n_bins x n_mels) float32 row-major matrix == MEL_FILTER_BANK_MATRIX.
+inline std::vector<float> make_mel_matrix(int sr, int n_fft, int n_mels, double fmin, double fmax) {
+    const int n_bins = n_fft / 2 + 1;
+    std::vector<double> mel_f(n_mels + 2);
+    const double lo = hz_to_mel(fmin), hi = hz_to_mel(fmax);
+    const double step = (hi - lo) / (n_mels + 1);
+    for (int i = 0; i < n_mels + 2; ++i) mel_f[i] = mel_to_hz(i == n_mels + 1 ? hi : lo + step * i);
+    const double val = 1.0 / (static_cast<double>(n_fft) * (1.0 / sr));      // np.fft.rfftfreq
+    std::vector<float> w(static_cast<size_t>(n_bins) * n_mels, 0.f);
+    for (int i = 0; i < n_mels; ++i) {
+        const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+        const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+        for (int k = 0; k < n_bins; ++k) {
+            const double fk = k * val;
+            const double lower = -(mel_f[i] - fk) / fd0;
+            const double upper = (mel_f[i + 2] - fk) / fd1;
+            const double tri = std::fmax(0.0, std::fmin(lower, upper));
+            const float tri32 = static_cast<float>(tri);
+            w[static_cast<size_t>(k) * n_mels + i] = static_cast<float>(static_cast<double>(tri32) * enorm);
+        }
+    }
+    return w;
+}
+
+struct MelBand {
+    int lo, cnt, woff, pad;
+};
+// Compact band form: per filter the contiguous run of non-zero weights.
+inline void make_mel_bands(const std::vector<float>& dense, int n_bins, int n_mels, std::vector<MelBand>& tab,
+                           std::vector<float>& weights) {
+    tab.resize(n_mels);
+    weights.clear();
+    for (int m = 0; m < n_mels; ++m) {
+        int first = -1, last = -1;
+        for (int k = 0; k < n_bins; ++k)
+            if (dense[static_cast<size_t>(k) * n_mels + m] != 0.f) {
+                if (first < 0) first = k;
+                last = k;
+            }
+        if (first < 0) { first = 0; last = -1; }
+        tab[m] = {first, last - first + 1, static_cast<int>(weights.size()), 0};
+        for (int k = first; k <= last; ++k) weights.push_back(dense[static_cast<size_t>(k) * n_mels + m]);
+        while (weights.size() % 4) weights.push_back(0.f);
+    }
+}
+
+}  // namespace sedb_host

@@ -1,0 +1,77 @@
+// One-CTA tcgen05 GEMM probe: pins the shared-memory descriptor conventions (K-major / MN-major canonical
+// no-swizzle layouts, LBO/SBO meaning, padded strides, negate bit) that the production kernels rely on.
+#pragma once
+#include "umma.cuh"
+
+namespace sedb {
+
+// D[128,N] = A[128,K] * B[K,N]; a/b/d float32 row-major in global memory.  K <= 64, N <= 256.
+__global__ void __launch_bounds__(128, 1) umma_probe_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                            float* __restrict__ d, int N, int K, int a_major,
+                                                            int b_major, int pad, int neg_b, int swap_fields) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_ptr;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    // operand A: MN = 128 rows; operand B: MN = N
+    const uint32_t sbo = 128 + pad;
+    const uint32_t a_lbo = (128 / 8) * sbo;
+    const uint32_t b_lbo = (N / 8) * sbo;
+    uint8_t* a_s = smem;
+    uint8_t* b_s = smem + (K / 8) * a_lbo;
+
+    for (int i = tid; i < 128 * K; i += 128) {
+        const int m = i / K, k = i % K;
+        const __nv_bfloat16 v = __float2bfloat16_rn(a[i]);
+        const uint32_t off = (m / 8) * sbo + (k / 8) * a_lbo +
+                             (a_major == 0 ? (m % 8) * 16 + (k % 8) * 2 : (k % 8) * 16 + (m % 8) * 2);
+        *reinterpret_cast<__nv_bfloat16*>(a_s + off) = v;
+    }
+    for (int i = tid; i < K * N; i += 128) {
+        const int k = i / N, n = i % N;
+        const __nv_bfloat16 v = __float2bfloat16_rn(b[i]);
+        const uint32_t off = (n / 8) * sbo + (k / 8) * b_lbo +
+                             (b_major == 0 ? (n % 8) * 16 + (k % 8) * 2 : (k % 8) * 16 + (n % 8) * 2);
+        *reinterpret_cast<__nv_bfloat16*>(b_s + off) = v;
+    }
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc<256>(&tmem_ptr);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_ptr;
+
+    if (tid == 0) {
+        const uint32_t idesc = make_idesc(kFmtBF16, a_major, b_major, 128, N, 0, neg_b);
+        for (int ks = 0; ks < K / 16; ++ks) {
+            const uint32_t a_addr = smem_u32(a_s) + ks * 2 * a_lbo;
+            const uint32_t b_addr = smem_u32(b_s) + ks * 2 * b_lbo;
+            const uint64_t da = swap_fields ? make_smem_desc(a_addr, sbo, a_lbo) : make_smem_desc(a_addr, a_lbo, sbo);
+            const uint64_t db = swap_fields ? make_smem_desc(b_addr, sbo, b_lbo) : make_smem_desc(b_addr, b_lbo, sbo);
+            umma_f16(tmem, da, db, idesc, ks > 0 ? 1u : 0u);
+        }
+        umma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after();
+    const uint32_t tl = tmem + (static_cast<uint32_t>(warp * 32) << 16);
+    for (int c0 = 0; c0 < N; c0 += 16) {
+        float v[16];
+        tmem_ld16(tl + c0, v);
+        tmem_ld_wait();
+        for (int i = 0; i < 16; ++i) d[(warp * 32 + lane) * N + c0 + i] = v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc<256>(tmem);
+    }
+}
+
+}  // namespace sedb

@@ -1,0 +1,317 @@
+// libsedb.so -- C ABI (include/sedb.h) over the hand-written sm_100a kernels.
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sedb.h"
+#include "host_tables.h"
+#include "logmel.cuh"
+#include "probe.cuh"
+#include "cnn.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+#define CUDA_TRY(expr)                                                                    \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess) return fail("%s: %s", #expr, cudaGetErrorString(e__));    \
+    } while (0)
+
+constexpr bool kFp16 = SEDB_SPLIT_FP16 != 0;
+
+}  // namespace
+
+struct sedb_ctx {
+    int device = -1;
+    int num_sms = 0;
+    uint8_t* a1 = nullptr;        // stage-1 DFT constants
+    uint8_t* b2 = nullptr;        // stage-2 DFT constants
+    float* mel_w = nullptr;       // compact mel weights
+    int4* mel_tab = nullptr;      // per-filter band table
+    // host-buffer pipeline state (sedb_logmel_host_f32 / sedb_sed_host_f32)
+    cudaStream_t s_copy = nullptr, s_comp = nullptr;
+    float* stage[2] = {nullptr, nullptr};
+    size_t stage_elems = 0;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr};
+    float* d_out = nullptr;
+    size_t d_out_elems = 0;
+    float* d_norm = nullptr;
+    void* d_ws = nullptr;
+    size_t d_ws_bytes = 0;
+    float* d_probs = nullptr;
+    size_t d_probs_elems = 0;
+};
+
+#include "cnn_host.inl"
+
+extern "C" {
+
+int sedb_version(void) { return SEDB_ABI_VERSION; }
+const char* sedb_last_error(void) { return g_err.c_str(); }
+int sedb_split_is_fp16(void) { return kFp16 ? 1 : 0; }
+long long sedb_launch_count(void) { return g_launches.load(); }
+
+int sedb_check_config(int sample_rate, int frame_size, int hop_size, int nfft, int mel_bins, float fmin, float fmax) {
+    if (sample_rate != SEDB_SAMPLE_RATE || frame_size != SEDB_FRAME_SIZE || hop_size != SEDB_HOP_SIZE ||
+        nfft != SEDB_NFFT || mel_bins != SEDB_MEL_BINS || fmin != SEDB_MEL_FMIN || fmax != SEDB_MEL_FMAX)
+        return fail("configuration mismatch: library is specialised for sr=%d frame=%d hop=%d nfft=%d mel=%d "
+                    "fmin=%g fmax=%g, caller has sr=%d frame=%d hop=%d nfft=%d mel=%d fmin=%g fmax=%g",
+                    SEDB_SAMPLE_RATE, SEDB_FRAME_SIZE, SEDB_HOP_SIZE, SEDB_NFFT, SEDB_MEL_BINS, SEDB_MEL_FMIN,
+                    SEDB_MEL_FMAX, sample_rate, frame_size, hop_size, nfft, mel_bins, fmin, fmax);
+    return 0;
+}
+
+long long sedb_num_frames(long long n_samples) { return 1 + n_samples / SEDB_HOP_SIZE; }
+
+int sedb_mel_filterbank(float* out_host) {
+    if (!out_host) return fail("sedb_mel_filterbank: null output");
+    std::vector<float> w = sedb_host::make_mel_matrix(SEDB_SAMPLE_RATE, SEDB_NFFT, SEDB_MEL_BINS, SEDB_MEL_FMIN,
+                                                      SEDB_MEL_FMAX);
+    std::memcpy(out_host, w.data(), w.size() * sizeof(float));
+    return 0;
+}
+
+int sedb_create(sedb_ctx_t** out_ctx) {
+    if (!out_ctx) return fail("sedb_create: null output");
+    *out_ctx = nullptr;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10)
+        return fail("sedb_create: device %d is sm_%d%d; this library contains sm_100a code only (no fallback)", dev,
+                    prop.major, prop.minor);
+    sedb_ctx* c = new (std::nothrow) sedb_ctx();
+    if (!c) return fail("sedb_create: out of host memory");
+    c->device = dev;
+    c->num_sms = prop.multiProcessorCount;
+    std::vector<uint8_t> a1 = sedb_host::make_stage1_constants(kFp16);
+    std::vector<uint8_t> b2 = sedb_host::make_stage2_constants(kFp16);
+    std::vector<float> dense = sedb_host::make_mel_matrix(SEDB_SAMPLE_RATE, SEDB_NFFT, SEDB_MEL_BINS, SEDB_MEL_FMIN,
+                                                          SEDB_MEL_FMAX);
+    std::vector<sedb_host::MelBand> tab;
+    std::vector<float> wts;
+    sedb_host::make_mel_bands(dense, SEDB_NUM_BINS, SEDB_MEL_BINS, tab, wts);
+    CUDA_TRY(cudaMalloc(&c->a1, a1.size()));
+    CUDA_TRY(cudaMalloc(&c->b2, b2.size()));
+    CUDA_TRY(cudaMalloc(&c->mel_w, wts.size() * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&c->mel_tab, tab.size() * sizeof(int4)));
+    CUDA_TRY(cudaMemcpy(c->a1, a1.data(), a1.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->b2, b2.data(), b2.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->mel_w, wts.data(), wts.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMemcpy(c->mel_tab, tab.data(), tab.size() * sizeof(int4), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaFuncSetAttribute(sedb::logmel_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  sedb::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(sedb::logmel_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  sedb::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(sedb::power_mel_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  68 * 1024));
+    if (int rc = sedb_cnn_kernels_init()) return rc;
+    *out_ctx = c;
+    return 0;
+}
+
+int sedb_destroy(sedb_ctx_t* c) {
+    if (!c) return 0;
+    cudaFree(c->a1);
+    cudaFree(c->b2);
+    cudaFree(c->mel_w);
+    cudaFree(c->mel_tab);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(c->stage[i]);
+        if (c->ev_h2d[i]) cudaEventDestroy(c->ev_h2d[i]);
+        if (c->ev_done[i]) cudaEventDestroy(c->ev_done[i]);
+    }
+    cudaFree(c->d_out);
+    cudaFree(c->d_norm);
+    cudaFree(c->d_ws);
+    cudaFree(c->d_probs);
+    if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    if (c->s_comp) cudaStreamDestroy(c->s_comp);
+    delete c;
+    return 0;
+}
+
+static int launch_logmel(sedb_ctx_t* c, int mode, const float* wave, long long n_clips, long long n_samples,
+                         long long wave_stride, const float* norm, float* out, float* spec, cudaStream_t st) {
+    if (!c) return fail("null context");
+    if (!wave || (mode == 0 ? !out : !spec)) return fail("null buffer");
+    if (n_clips < 0) return fail("negative clip count");
+    if (n_clips == 0) return 0;
+    if (n_samples <= sedb::kPadRefl)
+        return fail("n_samples=%lld: reflect padding (center=True, n_fft=%d) needs more than %d samples", n_samples,
+                    SEDB_NFFT, sedb::kPadRefl);
+    if (n_samples > 2000000000LL) return fail("n_samples too large");
+    if (wave_stride < n_samples) return fail("wave_stride < n_samples");
+    sedb::LogmelParams p;
+    p.wave = wave;
+    p.wave_stride = wave_stride;
+    p.n_samples = static_cast<int>(n_samples);
+    p.n_clips = static_cast<int>(n_clips);
+    p.n_frames = static_cast<int>(sedb_num_frames(n_samples));
+    p.a1 = c->a1;
+    p.b2 = c->b2;
+    p.mel_w = c->mel_w;
+    p.mel_tab = c->mel_tab;
+    p.norm = norm;
+    p.out = out;
+    p.spec = reinterpret_cast<float2*>(spec);
+    const long long total = n_clips * p.n_frames;
+    const int grid = static_cast<int>(total < c->num_sms ? total : c->num_sms);
+    if (mode == 0)
+        sedb::logmel_fused_kernel<0><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
+    else
+        sedb::logmel_fused_kernel<1><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int sedb_logmel_f32(sedb_ctx_t* ctx, const float* wave_dev, long long n_clips, long long n_samples,
+                    long long wave_stride, const float* norm_dev, float* out_dev, void* stream) {
+    return launch_logmel(ctx, 0, wave_dev, n_clips, n_samples, wave_stride, norm_dev, out_dev, nullptr,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int sedb_stft_c64(sedb_ctx_t* ctx, const float* wave_dev, long long n_clips, long long n_samples,
+                  long long wave_stride, float* spec_dev, void* stream) {
+    return launch_logmel(ctx, 1, wave_dev, n_clips, n_samples, wave_stride, nullptr, nullptr, spec_dev,
+                         static_cast<cudaStream_t>(stream));
+}
+
+int sedb_power_mel_db_f32(sedb_ctx_t* c, const float* spec_dev, long long rows, const float* norm_dev, float* out_dev,
+                          void* stream) {
+    if (!c) return fail("null context");
+    if (!spec_dev || !out_dev) return fail("null buffer");
+    if (rows < 0) return fail("negative row count");
+    if (rows == 0) return 0;
+    const int grid = static_cast<int>(rows < 4LL * c->num_sms ? rows : 4LL * c->num_sms);
+    sedb::power_mel_db_kernel<<<grid, 256, 68 * 1024, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2*>(spec_dev), rows, c->mel_w, c->mel_tab, norm_dev, out_dev);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+// ---- host-buffer pipelines -------------------------------------------------------------------------------
+static int ensure_pipeline(sedb_ctx_t* c, size_t stage_elems, size_t out_elems) {
+    if (!c->s_copy) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&c->s_comp, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+            CUDA_TRY(cudaEventCreateWithFlags(&c->ev_done[i], cudaEventDisableTiming));
+        }
+        CUDA_TRY(cudaMalloc(&c->d_norm, 2 * SEDB_MEL_BINS * sizeof(float)));
+    }
+    if (stage_elems > c->stage_elems) {
+        for (int i = 0; i < 2; ++i) {
+            cudaFree(c->stage[i]);
+            c->stage[i] = nullptr;
+            CUDA_TRY(cudaMalloc(&c->stage[i], stage_elems * sizeof(float)));
+        }
+        c->stage_elems = stage_elems;
+    }
+    if (out_elems > c->d_out_elems) {
+        cudaFree(c->d_out);
+        c->d_out = nullptr;
+        CUDA_TRY(cudaMalloc(&c->d_out, out_elems * sizeof(float)));
+        c->d_out_elems = out_elems;
+    }
+    return 0;
+}
+
+// Shared body: H2D in chunks of clips (double buffered) overlapped with the fused log-mel kernel; optional CNN
+// on the resident log-mel image; one D2H of the result.
+static int run_host_pipeline(sedb_ctx_t* c, sedb_cnn_t* cnn, const float* wave_host, long long n_clips,
+                             long long n_samples, long long wave_stride, const float* norm_host, float* result_host) {
+    if (!c) return fail("null context");
+    if (!wave_host || !result_host) return fail("null buffer");
+    if (n_clips <= 0) return n_clips == 0 ? 0 : fail("negative clip count");
+    if (n_samples <= sedb::kPadRefl) return fail("n_samples must exceed %d", sedb::kPadRefl);
+    if (wave_stride < n_samples) return fail("wave_stride < n_samples");
+    const long long T = sedb_num_frames(n_samples);
+    // chunk ~ 64 MB of waveform: long enough to saturate PCIe, short enough to overlap with compute
+    long long chunk = (64LL << 20) / (n_samples * 4);
+    if (chunk < 1) chunk = 1;
+    if (chunk > n_clips) chunk = n_clips;
+    const size_t samples_padded = (static_cast<size_t>(n_samples) + 3) & ~static_cast<size_t>(3);
+    if (int rc = ensure_pipeline(c, static_cast<size_t>(chunk) * samples_padded,
+                                 static_cast<size_t>(n_clips) * T * SEDB_MEL_BINS))
+        return rc;
+    const float* norm_dev = nullptr;
+    if (norm_host) {
+        CUDA_TRY(cudaMemcpyAsync(c->d_norm, norm_host, 2 * SEDB_MEL_BINS * sizeof(float), cudaMemcpyHostToDevice,
+                                 c->s_comp));
+        norm_dev = c->d_norm;
+    }
+    int buf = 0;
+    for (long long c0 = 0; c0 < n_clips; c0 += chunk, buf ^= 1) {
+        const long long nc = (n_clips - c0 < chunk) ? (n_clips - c0) : chunk;
+        // the staging buffer may still be read by the kernel launched two chunks ago
+        CUDA_TRY(cudaStreamWaitEvent(c->s_copy, c->ev_done[buf], 0));
+        CUDA_TRY(cudaMemcpy2DAsync(c->stage[buf], samples_padded * sizeof(float), wave_host + c0 * wave_stride,
+                                   static_cast<size_t>(wave_stride) * sizeof(float),
+                                   static_cast<size_t>(n_samples) * sizeof(float), static_cast<size_t>(nc),
+                                   cudaMemcpyHostToDevice, c->s_copy));
+        CUDA_TRY(cudaEventRecord(c->ev_h2d[buf], c->s_copy));
+        CUDA_TRY(cudaStreamWaitEvent(c->s_comp, c->ev_h2d[buf], 0));
+        if (int rc = launch_logmel(c, 0, c->stage[buf], nc, n_samples, static_cast<long long>(samples_padded), norm_dev,
+                                   c->d_out + c0 * T * SEDB_MEL_BINS, nullptr, c->s_comp))
+            return rc;
+        CUDA_TRY(cudaEventRecord(c->ev_done[buf], c->s_comp));
+    }
+    if (!cnn) {
+        CUDA_TRY(cudaMemcpyAsync(result_host, c->d_out, static_cast<size_t>(n_clips) * T * SEDB_MEL_BINS * sizeof(float),
+                                 cudaMemcpyDeviceToHost, c->s_comp));
+    } else {
+        if (int rc = sedb_cnn_forward_pipeline(c, cnn, n_clips, T, result_host)) return rc;
+    }
+    CUDA_TRY(cudaStreamSynchronize(c->s_comp));
+    return 0;
+}
+
+int sedb_logmel_host_f32(sedb_ctx_t* ctx, const float* wave_host, long long n_clips, long long n_samples,
+                         long long wave_stride, const float* norm_host, float* out_host) {
+    return run_host_pipeline(ctx, nullptr, wave_host, n_clips, n_samples, wave_stride, norm_host, out_host);
+}
+
+int sedb_sed_host_f32(sedb_ctx_t* ctx, sedb_cnn_t* cnn, const float* wave_host, long long n_clips,
+                      long long n_samples, long long wave_stride, const float* norm_host, float* probs_host) {
+    if (!cnn) return fail("null cnn handle");
+    return run_host_pipeline(ctx, cnn, wave_host, n_clips, n_samples, wave_stride, norm_host, probs_host);
+}
+
+int sedb_debug_umma_probe(const float* a_dev, const float* b_dev, float* d_dev, int N, int K, int a_major,
+                          int b_major, int pad, int neg_b, int swap_lbo_sbo, void* stream) {
+    if (!a_dev || !b_dev || !d_dev) return fail("null buffer");
+    if (N < 16 || N > 256 || N % 16 || K < 16 || K > 64 || K % 16 || pad < 0 || pad % 16)
+        return fail("probe supports N in [16,256] step 16, K in {16,32,48,64}, pad multiple of 16");
+    const int smem = (K / 8) * (16 + N / 8) * (128 + pad);
+    CUDA_TRY(cudaFuncSetAttribute(sedb::umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    sedb::umma_probe_kernel<<<1, 128, smem, static_cast<cudaStream_t>(stream)>>>(a_dev, b_dev, d_dev, N, K, a_major,
+                                                                                b_major, pad, neg_b, swap_lbo_sbo);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

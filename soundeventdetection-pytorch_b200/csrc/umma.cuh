@@ -1,0 +1,176 @@
+// Blackwell (sm_100a) primitives used by the SED kernels: tcgen05 MMA / TMEM, mbarrier,
+// bulk async copies (TMA engine), proxy fences.  Hand-written inline PTX; no CUTLASS.
+//
+// Canonical shared-memory operand layouts (SWIZZLE_NONE, 16-bit elements, 8x8 "core matrices" of
+// 128 contiguous bytes).  For an operand tile with MN rows/cols and a K extent:
+//
+//   K-major  : byte(mn,k) = (mn/8)*SBO + (k/8)*LBO + (mn%8)*16 + (k%8)*2      (8 K-elements contiguous)
+//   MN-major : byte(mn,k) = (mn/8)*SBO + (k/8)*LBO + (k%8)*16  + (mn%8)*2     (8 MN-elements contiguous)
+//
+// i.e. in both modes SBO strides between groups of 8 along MN and LBO between groups of 8 along K.
+// (Descriptor bit layout: start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48),
+//  layout_type [61,64) = 0 for no swizzle.)
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace sedb {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+// ------------------------------------------------------------------ mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU box.  On timeout (~seconds) the kernel traps,
+// which surfaces as a CUDA launch failure on the host instead of a wedged device.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("sedb: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
+                   smem_u32(bar), parity);
+            __trap();
+        }
+    }
+}
+
+// ------------------------------------------------------------------ proxy fences
+// generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / bulk copies)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+// ------------------------------------------------------------------ bulk copy global -> smem (TMA engine, 1-D)
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------ TMEM
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {   // one full warp
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_result)),
+                 "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {        // same warp that allocated
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// 32 lanes x 16 consecutive 32-bit columns: thread i of the warp gets lane (base_lane + i).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------ descriptors
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;   // descriptor version (Blackwell)
+    return d;                              // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+
+enum : uint32_t { kFmtF16 = 0, kFmtBF16 = 1 };
+enum : uint32_t { kMajorK = 0, kMajorMN = 1 };
+
+// kind::f16 instruction descriptor: fp32 accumulate, A/B formats, majors, optional negation, M and N.
+__host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt, uint32_t a_major, uint32_t b_major, uint32_t M,
+                                                  uint32_t N, uint32_t a_neg = 0, uint32_t b_neg = 0) {
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | (a_neg << 13) | (b_neg << 14) | (a_major << 15) |
+           (b_major << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                         uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Arrive on an mbarrier when all previously issued MMAs of this thread have completed.
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ------------------------------------------------------------------ split-precision helpers
+// x ~= hi + lo with both halves in a 16-bit float format; three MMAs (hi*hi + lo*hi + hi*lo) then
+// reproduce the fp32 product to ~2^-17 (bf16) / ~2^-22 (fp16) relative.
+#ifndef SEDB_SPLIT_FP16
+#define SEDB_SPLIT_FP16 0
+#endif
+#if SEDB_SPLIT_FP16
+typedef __half split_t;
+constexpr uint32_t kSplitFmt = kFmtF16;
+__device__ __forceinline__ split_t to_split(float x) { return __float2half_rn(x); }
+__device__ __forceinline__ float from_split(split_t h) { return __half2float(h); }
+#else
+typedef __nv_bfloat16 split_t;
+constexpr uint32_t kSplitFmt = kFmtBF16;
+__device__ __forceinline__ split_t to_split(float x) { return __float2bfloat16_rn(x); }
+__device__ __forceinline__ float from_split(split_t h) { return __bfloat162float(h); }
+#endif
+
+__device__ __forceinline__ uint32_t pack2(split_t a, split_t b) {
+    uint16_t ua = *reinterpret_cast<uint16_t*>(&a);
+    uint16_t ub = *reinterpret_cast<uint16_t*>(&b);
+    return static_cast<uint32_t>(ua) | (static_cast<uint32_t>(ub) << 16);
+}
+// split two floats, return packed hi pair and lo pair
+__device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    split_t h0 = to_split(x0), h1 = to_split(x1);
+    split_t l0 = to_split(x0 - from_split(h0)), l1 = to_split(x1 - from_split(h1));
+    hi = pack2(h0, h1);
+    lo = pack2(l0, l1);
+}
+
+}  // namespace sedb
