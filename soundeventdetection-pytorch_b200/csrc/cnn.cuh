@@ -1,2 +1,553 @@
+// Conv-BN-ReLU(-Pool) blocks of the reference CNNs as implicit-GEMM tcgen05 kernels (inference, BN folded).
+//
+//   ConvBlock / Cnn_AvgPooling   models/spectogram_models.py:128-205   (3x3 conv, BN2d, ReLU, AvgPool2d)
+//   M5                           models/waveform_models.py:9-71        (k=3 conv1d, BN1d, ReLU, MaxPool1d(4))
+//
+// Activation layout ("blocked planes"): per image, per split half (hi, lo), per group of 8 channels, a plane of
+// S pixels x 8 channels (16 B per pixel).  Pixels are indexed by the *padded* linear index
+// v = (h+1)*(W+2) + (w+1) (2-D) or v = pos+1 (1-D) behind `lead` zero pixels; padding pixels are zero and are
+// never written.  With this layout
+//   * one 1-D bulk copy (TMA engine) stages a K-group of a band of pixels (+halo) into shared memory, already in
+//     the tcgen05 canonical K-major layout (row = pixel, 16 B = 8 channels), and
+//   * the A operand of every filter tap is the same shared-memory patch with the descriptor start address
+//     shifted by (dh*(W+2)+dw) pixels -- no im2col copies.
+// GEMM view: M = pixels (128 per tile, up to 4 tiles per CTA pass), N = C_out tile (<=128), K = taps x C_in.
+// Operands are split bf16 hi/lo (3 MMAs per product, fp32 accumulation in TMEM) so that frame probabilities
+// stay within 1e-3 of the fp32 reference; BN scale/shift and ReLU are applied in fp32 in the epilogue.
 #pragma once
-// placeholder, replaced below
+#include "umma.cuh"
+
+namespace sedb {
+
+constexpr int kConvThreads = 320;          // 8 epilogue warps + MMA warp + copy warp
+constexpr int kConvWSlots = 6;
+constexpr int kConvWSlotBytes = 128 * 64;  // one (tap, 16-channel) weight block: hi|lo x [cout_tile][16]
+constexpr int kConvLead = 8;
+
+struct ConvParams {
+    const uint8_t* in;
+    uint8_t* out;
+    const uint8_t* wpack;
+    const float* scale;      // folded BN scale  [cout]
+    const float* shift;      // folded BN shift (+ conv bias) [cout]
+    int n_img, n_bands, n_tiles;
+    int mode;                // 0: 2-D 3x3, 1: 1-D k=3
+    int H, W, Wp;
+    int cin, cout, cin_chunk, n_kchunks, cout_tile, n_ntiles;
+    int S_in, S_out;
+    int R;                   // rows per band (2-D) ; positions per band = 128*n_tiles (1-D)
+    int P, halo;             // patch pixels, halo pixels in front of the band
+    int pool;                // 1 none, 2 avg 2x2 (2-D), 4 max 4 (1-D)
+    int Ho, Wo, Wpo;
+    int ntaps;
+    int tapoff[9];           // tap offsets in pixels relative to the patch start
+    int patch_bytes;         // 2 * (cin_chunk/8) * P * 16
+};
+
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
+
+__device__ __forceinline__ void store_split8(uint8_t* hi_ptr, uint8_t* lo_ptr, const float* y) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __nv_bfloat16 h0 = __float2bfloat16_rn(y[2 * i]), h1 = __float2bfloat16_rn(y[2 * i + 1]);
+        __nv_bfloat16 l0 = __float2bfloat16_rn(y[2 * i] - __bfloat162float(h0));
+        __nv_bfloat16 l1 = __float2bfloat16_rn(y[2 * i + 1] - __bfloat162float(h1));
+        h[i] = static_cast<uint32_t>(*reinterpret_cast<uint16_t*>(&h0)) |
+               (static_cast<uint32_t>(*reinterpret_cast<uint16_t*>(&h1)) << 16);
+        l[i] = static_cast<uint32_t>(*reinterpret_cast<uint16_t*>(&l0)) |
+               (static_cast<uint32_t>(*reinterpret_cast<uint16_t*>(&l1)) << 16);
+    }
+    *reinterpret_cast<uint4*>(hi_ptr) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo_ptr) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// shared memory: [patch | weight ring | scale/shift | barriers | tmem ptr]; the pooling stage aliases the patch.
+__global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvParams p) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* patch = smem;
+    uint8_t* wring = smem + ((p.patch_bytes + 127) / 128) * 128;
+    float* sc_s = reinterpret_cast<float*>(wring + kConvWSlots * kConvWSlotBytes);
+    float* sh_s = sc_s + p.cout;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(
+        (reinterpret_cast<uintptr_t>(sh_s + p.cout) + 15) & ~static_cast<uintptr_t>(15));
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 24);
+    float* stage = reinterpret_cast<float*>(patch);
+
+    uint64_t* wfull = bars + 0;        // [6]
+    uint64_t* wempty = bars + 6;       // [6]
+    uint64_t* patch_full = bars + 12;
+    uint64_t* patch_free = bars + 13;
+    uint64_t* acc_full = bars + 14;
+    uint64_t* epi_done = bars + 15;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        for (int s = 0; s < kConvWSlots; ++s) {
+            mbar_init(&wfull[s], 1);
+            mbar_init(&wempty[s], 1);
+        }
+        mbar_init(patch_full, 1);
+        mbar_init(patch_free, 1);
+        mbar_init(acc_full, 1);
+        mbar_init(epi_done, 8);
+        mbar_fence_init();
+    }
+    if (warp == 8) tmem_alloc<512>(tmem_ptr_s);
+    for (int i = tid; i < p.cout; i += kConvThreads) {
+        sc_s[i] = p.scale[i];
+        sh_s[i] = p.shift[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr_s;
+
+    const int items_total = p.n_img * p.n_bands * p.n_ntiles;
+    const int n_items = (static_cast<int>(blockIdx.x) < items_total)
+                            ? (items_total - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                                  static_cast<int>(gridDim.x)
+                            : 0;
+    const int kg_chunk = p.cin_chunk / 8;
+    const int ks_chunk = p.cin_chunk / 16;
+    const int wblock_bytes = p.cout_tile * 64;
+    const int blocks_per_kc = p.ntaps * ks_chunk;
+
+    auto decode = [&](int it, int& img, int& band, int& ntile) {
+        int item = blockIdx.x + it * gridDim.x;
+        ntile = item % p.n_ntiles;
+        item /= p.n_ntiles;
+        band = item % p.n_bands;
+        img = item / p.n_bands;
+    };
+    auto band_v0 = [&](int band) { return p.mode == 0 ? (p.R * band + 1) * p.Wp : 1 + band * 128 * p.n_tiles; };
+
+    if (warp == 9) {
+        // ================================================================ bulk-copy producer
+        if (lane == 0) {
+            int gw = 0;
+            for (int it = 0; it < n_items; ++it) {
+                int img, band, ntile;
+                decode(it, img, band, ntile);
+                const int v0 = band_v0(band);
+                for (int kc = 0; kc < p.n_kchunks; ++kc) {
+                    const int gk = it * p.n_kchunks + kc;
+                    if (gk > 0) mbar_wait(patch_free, (gk - 1) & 1);
+                    if (kc == 0 && it > 0) mbar_wait(epi_done, (it - 1) & 1);
+                    mbar_arrive_expect_tx(patch_full, p.patch_bytes);
+                    for (int arr = 0; arr < 2; ++arr)
+                        for (int kgl = 0; kgl < kg_chunk; ++kgl) {
+                            const long long plane = (static_cast<long long>(img) * 2 + arr) * (p.cin / 8) + kc * kg_chunk + kgl;
+                            const uint8_t* src = p.in + (plane * p.S_in + kConvLead + v0 - p.halo) * 16;
+                            bulk_g2s(patch + (arr * kg_chunk + kgl) * p.P * 16, src, p.P * 16, patch_full);
+                        }
+                    const uint8_t* wsrc = p.wpack + static_cast<long long>(ntile * p.n_kchunks + kc) * blocks_per_kc * wblock_bytes;
+                    for (int b = 0; b < blocks_per_kc; ++b, ++gw) {
+                        const int s = gw % kConvWSlots, u = gw / kConvWSlots;
+                        mbar_wait(&wempty[s], (u & 1) ^ 1);
+                        mbar_arrive_expect_tx(&wfull[s], wblock_bytes);
+                        bulk_g2s(wring + s * kConvWSlotBytes, wsrc + static_cast<long long>(b) * wblock_bytes, wblock_bytes, &wfull[s]);
+                    }
+                }
+            }
+        }
+    } else if (warp == 8) {
+        // ================================================================ MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = make_idesc(kFmtBF16, kMajorK, kMajorK, 128, p.cout_tile);
+            const uint32_t patch_a = smem_u32(patch);
+            const uint32_t wring_a = smem_u32(wring);
+            const uint32_t a_lbo = p.P * 16;
+            const uint32_t b_lbo = p.cout_tile * 16;
+            const uint32_t lo_arr = kg_chunk * p.P * 16;       // offset of the lo half of the patch
+            int gw = 0;
+            for (int it = 0; it < n_items; ++it) {
+                if (it > 0) {
+                    mbar_wait(epi_done, (it - 1) & 1);
+                    tc_fence_after();
+                }
+                for (int kc = 0; kc < p.n_kchunks; ++kc) {
+                    const int gk = it * p.n_kchunks + kc;
+                    mbar_wait(patch_full, gk & 1);
+                    tc_fence_after();
+                    for (int b = 0; b < blocks_per_kc; ++b, ++gw) {
+                        const int tap = b / ks_chunk, ks = b % ks_chunk;
+                        const int s = gw % kConvWSlots, u = gw / kConvWSlots;
+                        mbar_wait(&wfull[s], u & 1);
+                        tc_fence_after();
+                        const uint32_t wb = wring_a + s * kConvWSlotBytes;
+                        const uint64_t bH = make_smem_desc(wb, b_lbo, 128);
+                        const uint64_t bL = make_smem_desc(wb + p.cout_tile * 32, b_lbo, 128);
+                        const uint32_t acc = (kc > 0 || b > 0) ? 1u : 0u;
+                        for (int m = 0; m < p.n_tiles; ++m) {
+                            const uint32_t a_addr = patch_a + (2 * ks * p.P + 128 * m + p.tapoff[tap]) * 16;
+                            const uint64_t aH = make_smem_desc(a_addr, a_lbo, 128);
+                            const uint64_t aL = make_smem_desc(a_addr + lo_arr, a_lbo, 128);
+                            const uint32_t d = tmem + m * p.cout_tile;
+                            umma_f16(d, aH, bH, idesc, acc);
+                            umma_f16(d, aL, bH, idesc, 1u);
+                            umma_f16(d, aH, bL, idesc, 1u);
+                        }
+                        umma_commit(&wempty[s]);
+                    }
+                    umma_commit(patch_free);
+                }
+                umma_commit(acc_full);
+            }
+        }
+    } else {
+        // ================================================================ epilogue warps
+        const int q = warp & 3, grp = warp >> 2;
+        const uint32_t tlane = tmem + (static_cast<uint32_t>(q * 32) << 16);
+        const int etid = tid;                                     // 0..255
+        for (int it = 0; it < n_items; ++it) {
+            int img, band, ntile;
+            decode(it, img, band, ntile);
+            const int v0 = band_v0(band);
+            const int n0 = ntile * p.cout_tile;
+            // number of valid band pixels
+            int rows_eff = 1, npix;
+            if (p.mode == 0) {
+                rows_eff = min(p.R, p.H - p.R * band);
+                npix = rows_eff * p.Wp;
+            } else {
+                npix = min(128 * p.n_tiles, p.W - band * 128 * p.n_tiles);
+            }
+            mbar_wait(acc_full, it & 1);
+            tc_fence_after();
+            const long long out_img = static_cast<long long>(img) * 2 * (p.cout / 8);
+            if (p.pool == 1) {
+                for (int m = grp; m < p.n_tiles; m += 2) {
+                    const int pp = 128 * m + 32 * q + lane;
+                    bool valid = pp < npix;
+                    if (p.mode == 0) {
+                        const int col = pp % p.Wp;
+                        valid = valid && col >= 1 && col <= p.W;
+                    }
+                    const long long vout = kConvLead + v0 + pp;
+                    for (int c0 = 0; c0 < p.cout_tile; c0 += 16) {
+                        float acc[16];
+                        tmem_ld16(tlane + m * p.cout_tile + c0, acc);
+                        tmem_ld_wait();
+                        if (valid) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i)
+                                acc[i] = fmaxf(0.f, fmaf(acc[i], sc_s[n0 + c0 + i], sh_s[n0 + c0 + i]));
+#pragma unroll
+                            for (int g2 = 0; g2 < 2; ++g2) {
+                                const long long kg = (n0 + c0) / 8 + g2;
+                                uint8_t* hi = p.out + ((out_img + kg) * p.S_out + vout) * 16;
+                                uint8_t* lo = p.out + ((out_img + (p.cout / 8) + kg) * p.S_out + vout) * 16;
+                                store_split8(hi, lo, acc + 8 * g2);
+                            }
+                        }
+                    }
+                }
+            } else {
+                // pooled: stage 16 channels of every band pixel, then reduce windows
+                for (int c0 = 0; c0 < p.cout_tile; c0 += 16) {
+                    for (int m = grp; m < p.n_tiles; m += 2) {
+                        const int pp = 128 * m + 32 * q + lane;
+                        float acc[16];
+                        tmem_ld16(tlane + m * p.cout_tile + c0, acc);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i)
+                            stage[pp * 17 + i] = fmaxf(0.f, fmaf(acc[i], sc_s[n0 + c0 + i], sh_s[n0 + c0 + i]));
+                    }
+                    epi_sync();
+                    if (p.mode == 0) {
+                        // avg 2x2: item = (pooled pixel, 8-channel half)
+                        const int half = etid & 1, pix = etid >> 1;
+                        const int r2 = pix / p.Wo, w2 = pix % p.Wo;
+                        const int ho = (p.R / 2) * band + r2;
+                        if (r2 < rows_eff / 2 && ho < p.Ho) {
+                            const int base = (2 * r2) * p.Wp + 2 * w2 + 1;
+                            float y[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int c = half * 8 + i;
+                                y[i] = 0.25f * (stage[base * 17 + c] + stage[(base + 1) * 17 + c] +
+                                                stage[(base + p.Wp) * 17 + c] + stage[(base + p.Wp + 1) * 17 + c]);
+                            }
+                            const long long vout = kConvLead + (ho + 1) * p.Wpo + w2 + 1;
+                            const long long kg = (n0 + c0) / 8 + half;
+                            uint8_t* hi = p.out + ((out_img + kg) * p.S_out + vout) * 16;
+                            uint8_t* lo = p.out + ((out_img + (p.cout / 8) + kg) * p.S_out + vout) * 16;
+                            store_split8(hi, lo, y);
+                        }
+                    } else {
+                        // max over 4 consecutive positions: item = (pooled position, 8-channel half)
+                        const int half = etid & 1, pos2 = etid >> 1;        // up to 128 pooled positions per band
+                        const int po = band * 32 * p.n_tiles + pos2;
+                        if (pos2 < 32 * p.n_tiles && po < p.Wo) {
+                            float y[8];
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const int c = half * 8 + i;
+                                const int b0 = 4 * pos2;
+                                y[i] = fmaxf(fmaxf(stage[b0 * 17 + c], stage[(b0 + 1) * 17 + c]),
+                                             fmaxf(stage[(b0 + 2) * 17 + c], stage[(b0 + 3) * 17 + c]));
+                            }
+                            const long long vout = kConvLead + 1 + po;
+                            const long long kg = (n0 + c0) / 8 + half;
+                            uint8_t* hi = p.out + ((out_img + kg) * p.S_out + vout) * 16;
+                            uint8_t* lo = p.out + ((out_img + (p.cout / 8) + kg) * p.S_out + vout) * 16;
+                            store_split8(hi, lo, y);
+                        }
+                    }
+                    epi_sync();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(epi_done);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// First layer of Cnn_AvgPooling (C_in = audio_channels = 1, K = 9): CUDA cores, fp32, writes blocked planes.
+// x: [n_img, H, W] fp32; w: [cout][9]; one thread per output pixel.
+__global__ void __launch_bounds__(256) conv_in2d_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                                        uint8_t* __restrict__ out, int n_img, int H, int W, int cout,
+                                                        int S_out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    float* w_s = reinterpret_cast<float*>(smem);     // [cout][9]
+    float* sc_s = w_s + cout * 9;
+    float* sh_s = sc_s + cout;
+    for (int i = threadIdx.x; i < cout * 9; i += blockDim.x) w_s[i] = w[i];
+    for (int i = threadIdx.x; i < cout; i += blockDim.x) {
+        sc_s[i] = scale[i];
+        sh_s[i] = shift[i];
+    }
+    __syncthreads();
+    const long long total = static_cast<long long>(n_img) * H * W;
+    const int Wp = W + 2;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int wq = static_cast<int>(idx % W);
+        const int h = static_cast<int>((idx / W) % H);
+        const int img = static_cast<int>(idx / (static_cast<long long>(W) * H));
+        const float* xi = x + static_cast<long long>(img) * H * W;
+        float v[9];
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh)
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int hh = h + kh - 1, ww = wq + kw - 1;
+                v[kh * 3 + kw] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xi + hh * W + ww) : 0.f;
+            }
+        const long long vout = kConvLead + (h + 1) * Wp + wq + 1;
+        const long long out_img = static_cast<long long>(img) * 2 * (cout / 8);
+        for (int kg = 0; kg < cout / 8; ++kg) {
+            float y[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int c = kg * 8 + i;
+                float a = 0.f;
+#pragma unroll
+                for (int t = 0; t < 9; ++t) a = fmaf(v[t], w_s[c * 9 + t], a);
+                y[i] = fmaxf(0.f, fmaf(a, sc_s[c], sh_s[c]));
+            }
+            uint8_t* hi = out + ((out_img + kg) * S_out + vout) * 16;
+            uint8_t* lo = out + ((out_img + (cout / 8) + kg) * S_out + vout) * 16;
+            store_split8(hi, lo, y);
+        }
+    }
+}
+
+// Head of Cnn_AvgPooling (spectogram_models.py:193-205): mean over freq, Linear, sigmoid, x ratio time repeat.
+// One warp per (image, time step).  in: blocked planes of the last block (C, Hf, Wf).
+__global__ void __launch_bounds__(256) head2d_kernel(const uint8_t* __restrict__ in, const float* __restrict__ fc_w,
+                                                     const float* __restrict__ fc_b, float* __restrict__ logits,
+                                                     float* __restrict__ probs, int n_img, int C, int Hf, int Wf,
+                                                     int S_in, int classes, int ratio) {
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp_global >= n_img * Hf) return;
+    const int img = warp_global / Hf, h = warp_global % Hf;
+    const int Wp = Wf + 2;
+    const long long img_base = static_cast<long long>(img) * 2 * (C / 8);
+    for (int cls = 0; cls < classes; ++cls) {
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const int kg = c >> 3, ci = c & 7;
+            float s = 0.f;
+            for (int wq = 0; wq < Wf; ++wq) {
+                const long long v = kConvLead + (h + 1) * Wp + wq + 1;
+                const __nv_bfloat16* ph = reinterpret_cast<const __nv_bfloat16*>(in + ((img_base + kg) * S_in + v) * 16);
+                const __nv_bfloat16* pl =
+                    reinterpret_cast<const __nv_bfloat16*>(in + ((img_base + C / 8 + kg) * S_in + v) * 16);
+                s += __bfloat162float(ph[ci]) + __bfloat162float(pl[ci]);
+            }
+            acc = fmaf(s * (1.0f / static_cast<float>(Wf)), fc_w[cls * C + c], acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        acc += fc_b[cls];
+        const float pr = 1.0f / (1.0f + __expf(-acc));
+        for (int r = lane; r < ratio; r += 32) {
+            const long long o = (static_cast<long long>(img) * Hf * ratio + static_cast<long long>(h) * ratio + r) * classes + cls;
+            if (logits) logits[o] = acc;
+            if (probs) probs[o] = pr;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// M5 conv_block1 (waveform_models.py:14-19): Conv1d(1->64, k=79, s=4, p=39) + BN + ReLU + MaxPool1d(4), CUDA
+// cores, fp32.  grid = (tiles of kIn1dTile pooled positions, frames); one warp per pooled position, each lane
+// owns two output channels.  Writes blocked planes (C = 64).
+constexpr int kIn1dTile = 64;
+constexpr int kIn1dSeg = 16 * kIn1dTile + 80;                         // input samples needed by one tile
+constexpr int kIn1dSmem = (79 * 64 + kIn1dSeg + 128) * 4;
+
+__global__ void __launch_bounds__(256) conv_in1d_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                        const float* __restrict__ scale, const float* __restrict__ shift,
+                                                        uint8_t* __restrict__ out, int L_in, int L_out, int S_out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    float* w_s = reinterpret_cast<float*>(smem);          // [79][64]  (tap-major: lanes read consecutive channels)
+    float* x_s = w_s + 79 * 64;                           // [kIn1dSeg]
+    float* sc_s = x_s + kIn1dSeg;
+    float* sh_s = sc_s + 64;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int frame = blockIdx.y;
+    const int j0 = blockIdx.x * kIn1dTile;
+    for (int i = tid; i < 79 * 64; i += 256) {
+        const int c = i / 79, t = i % 79;
+        w_s[t * 64 + c] = w[i];
+    }
+    if (tid < 64) {
+        sc_s[tid] = scale[tid];
+        sh_s[tid] = shift[tid];
+    }
+    const float* xf = x + static_cast<long long>(frame) * L_in;
+    const int x0 = 16 * j0 - 39;
+    for (int i = tid; i < kIn1dSeg; i += 256) {
+        const int g = x0 + i;
+        x_s[i] = (g >= 0 && g < L_in) ? __ldg(xf + g) : 0.f;
+    }
+    __syncthreads();
+    const int c0 = 2 * lane;
+    const float s0 = sc_s[c0], s1 = sc_s[c0 + 1], b0 = sh_s[c0], b1 = sh_s[c0 + 1];
+    for (int jl = warp; jl < kIn1dTile; jl += 8) {
+        const int j = j0 + jl;
+        if (j >= L_out) break;
+        float a[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
+        const float* xs = x_s + 16 * jl;
+#pragma unroll 4
+        for (int t = 0; t < 79; ++t) {
+            const float2 wv = *reinterpret_cast<const float2*>(w_s + t * 64 + c0);
+#pragma unroll
+            for (int ps = 0; ps < 4; ++ps) {
+                const float xv = xs[4 * ps + t];
+                a[ps][0] = fmaf(xv, wv.x, a[ps][0]);
+                a[ps][1] = fmaf(xv, wv.y, a[ps][1]);
+            }
+        }
+        float y0 = 0.f, y1 = 0.f;                                    // ReLU output is >= 0
+#pragma unroll
+        for (int ps = 0; ps < 4; ++ps) {
+            y0 = fmaxf(y0, fmaf(a[ps][0], s0, b0));
+            y1 = fmaxf(y1, fmaf(a[ps][1], s1, b1));
+        }
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
+        const long long v = kConvLead + 1 + j;
+        const long long img = static_cast<long long>(frame) * 2 * 8;
+        const int kg = lane >> 2, sub = (lane & 3) * 4;
+        uint8_t* hi = out + ((img + kg) * S_out + v) * 16 + sub;
+        uint8_t* lo = out + ((img + 8 + kg) * S_out + v) * 16 + sub;
+        *reinterpret_cast<uint32_t*>(hi) = static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&h0)) |
+                                           (static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&h1)) << 16);
+        *reinterpret_cast<uint32_t*>(lo) = static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&l0)) |
+                                           (static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&l1)) << 16);
+    }
+}
+
+// Head of M5 (waveform_models.py:66-67): mean over time, Linear.  One warp per frame.
+__global__ void __launch_bounds__(256) head1d_kernel(const uint8_t* __restrict__ in, const float* __restrict__ fc_w,
+                                                     const float* __restrict__ fc_b, float* __restrict__ logits,
+                                                     int n, int C, int Lf, int S_in, int classes) {
+    const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wg >= n) return;
+    const long long img_base = static_cast<long long>(wg) * 2 * (C / 8);
+    for (int cls = 0; cls < classes; ++cls) {
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32) {
+            const int kg = c >> 3, ci = c & 7;
+            float s = 0.f;
+            for (int pos = 0; pos < Lf; ++pos) {
+                const long long v = kConvLead + 1 + pos;
+                const __nv_bfloat16* ph = reinterpret_cast<const __nv_bfloat16*>(in + ((img_base + kg) * S_in + v) * 16);
+                const __nv_bfloat16* pl =
+                    reinterpret_cast<const __nv_bfloat16*>(in + ((img_base + C / 8 + kg) * S_in + v) * 16);
+                s += __bfloat162float(ph[ci]) + __bfloat162float(pl[ci]);
+            }
+            acc = fmaf(s * (1.0f / static_cast<float>(Lf)), fc_w[cls * C + c], acc);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) logits[static_cast<long long>(wg) * classes + cls] = acc + fc_b[cls];
+    }
+}
+
+// ---- parameter preparation ---------------------------------------------------------------------------
+// BN fold: scale = gamma / sqrt(var + eps), shift = beta - mean*scale (+ bias*scale)
+__global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var,
+                               const float* __restrict__ bias, float eps, int n, float* __restrict__ scale,
+                               float* __restrict__ shift) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float s = gamma[i] / sqrtf(var[i] + eps);
+    scale[i] = s;
+    shift[i] = beta[i] - mean[i] * s + (bias ? bias[i] * s : 0.f);
+}
+
+// Conv weight [cout][cin][ntaps] fp32 -> blocks [ntile][kc][tap][ks] of {hi,lo} x canonical K-major [cout_tile][16]
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int cout, int cin,
+                                        int ntaps, int cout_tile, int cin_chunk) {
+    const long long total = static_cast<long long>(cout) * cin * ntaps;
+    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (idx >= total) return;
+    const int tap = static_cast<int>(idx % ntaps);
+    const int ci = static_cast<int>((idx / ntaps) % cin);
+    const int co = static_cast<int>(idx / (static_cast<long long>(ntaps) * cin));
+    const float v = w[idx];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    const int ntile = co / cout_tile, n = co % cout_tile;
+    const int kc = ci / cin_chunk, cil = ci % cin_chunk;
+    const int ks = cil / 16, k = cil % 16;
+    const int n_kchunks = cin / cin_chunk, ks_chunk = cin_chunk / 16;
+    const long long block = ((static_cast<long long>(ntile) * n_kchunks + kc) * ntaps + tap) * ks_chunk + ks;
+    const long long base = block * (cout_tile * 64);
+    const int off = (k / 8) * (cout_tile * 16) + n * 16 + (k % 8) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(out + base + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(out + base + cout_tile * 32 + off) = l;
+}
+
+// Workspace hygiene: padding pixels of every activation plane must be zero.  The first word of the workspace
+// holds a tag describing the geometry it was zeroed for; when it matches nothing is done.
+__global__ void ws_zero_kernel(uint4* __restrict__ ws, long long n16, unsigned long long tag) {
+    const unsigned long long cur = *reinterpret_cast<const volatile unsigned long long*>(ws);
+    if (cur == tag) return;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x + 1; i < n16;
+         i += static_cast<long long>(gridDim.x) * blockDim.x)
+        ws[i] = z;
+}
+__global__ void ws_tag_kernel(unsigned long long* ws, unsigned long long tag) { ws[0] = tag; ws[1] = 0ull; }
+
+}  // namespace sedb

@@ -1,18 +1,558 @@
-// placeholder
-struct sedb_cnn { int dummy; };
-struct sedb_m5 { int dummy; };
-static int sedb_cnn_kernels_init() { return 0; }
-static int sedb_cnn_forward_pipeline(sedb_ctx_t*, sedb_cnn_t*, long long, long long, float*) { return fail("cnn not built"); }
-extern "C" {
-int sedb_cnn_create(sedb_ctx_t*, const int*, const int*, int, int, sedb_cnn_t**) { return fail("nyi"); }
-int sedb_cnn_destroy(sedb_cnn_t*) { return 0; }
-int sedb_cnn_load(sedb_cnn_t*, const float* const*, int, void*) { return fail("nyi"); }
-long long sedb_cnn_out_frames(const sedb_cnn_t*, long long) { return 0; }
-size_t sedb_cnn_workspace_bytes(const sedb_cnn_t*, long long, long long) { return 0; }
-int sedb_cnn_forward(sedb_cnn_t*, const float*, long long, long long, float*, float*, void*, size_t, void*) { return fail("nyi"); }
-int sedb_m5_create(sedb_ctx_t*, int, sedb_m5_t**) { return fail("nyi"); }
-int sedb_m5_destroy(sedb_m5_t*) { return 0; }
-int sedb_m5_load(sedb_m5_t*, const float* const*, int, void*) { return fail("nyi"); }
-size_t sedb_m5_workspace_bytes(const sedb_m5_t*, long long) { return 0; }
-int sedb_m5_forward(sedb_m5_t*, const float*, long long, float*, void*, size_t, void*) { return fail("nyi"); }
+// Host side of the CNN paths (included by sedb.cu): handles, geometry planning, parameter packing, launches.
+
+namespace {
+
+struct PlaneGeom {          // one blocked activation buffer
+    int C = 0, H = 0, W = 0;
+    int S = 0;              // pixels per 8-channel plane (incl. lead/tail slack)
+    size_t offset = 0;      // byte offset inside the workspace
+    size_t bytes_per_img() const { return static_cast<size_t>(2) * (C / 8) * S * 16; }
+};
+
+struct UmmaLayer {          // a conv layer executed by conv_umma_kernel
+    int cin = 0, cout = 0, pool = 1, mode = 0, ntaps = 9;
+    uint8_t* wpack = nullptr;
+    float* scale = nullptr;
+    float* shift = nullptr;
+    int cin_chunk = 0, cout_tile = 0;
+};
+
+int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+// Fills the launch parameters of one tensor-core conv layer for an input of H x W (2-D) or length W (1-D) and
+// returns the plane size S the *input* buffer must have.
+int plan_umma_layer(const UmmaLayer& L, int H, int W, sedb::ConvParams& p) {
+    p = sedb::ConvParams{};
+    p.mode = L.mode;
+    p.H = H;
+    p.W = W;
+    p.Wp = W + 2;
+    p.cin = L.cin;
+    p.cout = L.cout;
+    p.cin_chunk = L.cin_chunk;
+    p.n_kchunks = L.cin / L.cin_chunk;
+    p.cout_tile = L.cout_tile;
+    p.n_ntiles = L.cout / L.cout_tile;
+    p.pool = L.pool;
+    p.ntaps = L.ntaps;
+    const int max_tiles = (L.cin_chunk <= 64) ? 4 : 2;
+    if (L.mode == 0) {
+        p.halo = p.Wp + 1;
+        int R = (128 * max_tiles) / p.Wp;
+        if (L.pool == 2) R &= ~1;
+        const int Hcap = (L.pool == 2) ? round_up(H, 2) : H;
+        if (R > Hcap) R = Hcap;
+        if (R < L.pool) return -1;
+        p.R = R;
+        p.n_tiles = (R * p.Wp + 127) / 128;
+        p.n_bands = (H + R - 1) / R;
+        for (int kh = 0; kh < 3; ++kh)
+            for (int kw = 0; kw < 3; ++kw) p.tapoff[kh * 3 + kw] = p.halo + (kh - 1) * p.Wp + (kw - 1);
+        p.Ho = H / L.pool;
+        p.Wo = W / L.pool;
+        p.Wpo = p.Wo + 2;
+    } else {
+        p.halo = 1;
+        p.n_tiles = (W + 127) / 128;
+        if (p.n_tiles > max_tiles) p.n_tiles = max_tiles;
+        p.R = 0;
+        p.n_bands = (W + 128 * p.n_tiles - 1) / (128 * p.n_tiles);
+        for (int k = 0; k < 3; ++k) p.tapoff[k] = k;
+        p.Ho = 1;
+        p.Wo = W / L.pool;
+        p.Wpo = p.Wo + 2;
+    }
+    p.P = 128 * p.n_tiles + 2 * p.halo;
+    p.patch_bytes = 2 * (L.cin_chunk / 8) * p.P * 16;
+    const int v0_last = (L.mode == 0) ? (p.R * (p.n_bands - 1) + 1) * p.Wp : 1 + (p.n_bands - 1) * 128 * p.n_tiles;
+    return round_up(sedb::kConvLead + v0_last - p.halo + p.P, 8);
 }
+
+size_t conv_smem_bytes(const sedb::ConvParams& p) {
+    size_t patch = static_cast<size_t>(p.patch_bytes);
+    const size_t stage = static_cast<size_t>(128) * p.n_tiles * 17 * 4;
+    if (p.pool != 1 && patch < stage) patch = stage;
+    patch = (patch + 127) / 128 * 128;
+    return patch + sedb::kConvWSlots * sedb::kConvWSlotBytes + static_cast<size_t>(2) * p.cout * 4 + 16 + 24 * 8 + 16 + 128;
+}
+
+int final_plane_S(int mode, int H, int W) {
+    return round_up(sedb::kConvLead + (mode == 0 ? (H + 2) * (W + 2) : W + 2) + 8, 8);
+}
+
+int alloc_layer_params(UmmaLayer& L) {
+    L.cin_chunk = L.cin > 128 ? 128 : L.cin;
+    L.cout_tile = L.cout > 128 ? 128 : L.cout;
+    if (L.cin % 16 || L.cin % L.cin_chunk || L.cout % 16 || L.cout % L.cout_tile)
+        return fail("conv layer %d->%d: channel counts must be multiples of 16 (and of 128 above 128)", L.cin, L.cout);
+    CUDA_TRY(cudaMalloc(&L.wpack, static_cast<size_t>(L.cout) * L.cin * L.ntaps * 4));
+    CUDA_TRY(cudaMalloc(&L.scale, L.cout * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&L.shift, L.cout * sizeof(float)));
+    return 0;
+}
+void free_layer_params(UmmaLayer& L) {
+    cudaFree(L.wpack);
+    cudaFree(L.scale);
+    cudaFree(L.shift);
+    L.wpack = nullptr;
+    L.scale = L.shift = nullptr;
+}
+
+int launch_umma_layer(const sedb_ctx* c, const UmmaLayer& L, sedb::ConvParams p, const uint8_t* in, uint8_t* out,
+                      int n_img, int S_in, int S_out, cudaStream_t st) {
+    p.in = in;
+    p.out = out;
+    p.wpack = L.wpack;
+    p.scale = L.scale;
+    p.shift = L.shift;
+    p.n_img = n_img;
+    p.S_in = S_in;
+    p.S_out = S_out;
+    const long long items = static_cast<long long>(n_img) * p.n_bands * p.n_ntiles;
+    if (items <= 0) return 0;
+    const int grid = static_cast<int>(items < c->num_sms ? items : c->num_sms);
+    const size_t smem = conv_smem_bytes(p);
+    if (smem > 227 * 1024) return fail("conv layer needs %zu bytes of shared memory", smem);
+    sedb::conv_umma_kernel<<<grid, sedb::kConvThreads, smem, st>>>(p);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int fold_and_pack(UmmaLayer& L, const float* w, const float* bias, const float* gamma, const float* beta,
+                  const float* mean, const float* var, cudaStream_t st) {
+    const long long total = static_cast<long long>(L.cout) * L.cin * L.ntaps;
+    sedb::pack_conv_weight_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(w, L.wpack, L.cout, L.cin,
+                                                                                      L.ntaps, L.cout_tile, L.cin_chunk);
+    sedb::bn_fold_kernel<<<(L.cout + 127) / 128, 128, 0, st>>>(gamma, beta, mean, var, bias, 1e-5f, L.cout, L.scale,
+                                                              L.shift);
+    g_launches.fetch_add(2);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+int prepare_workspace(void* ws, size_t bytes, unsigned long long tag, cudaStream_t st) {
+    sedb::ws_zero_kernel<<<1184, 256, 0, st>>>(reinterpret_cast<uint4*>(ws), static_cast<long long>(bytes / 16), tag);
+    sedb::ws_tag_kernel<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long*>(ws), tag);
+    g_launches.fetch_add(2);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+unsigned long long mix_tag(unsigned long long h, unsigned long long v) {
+    h ^= v + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    return h;
+}
+
+}  // namespace
+
+// ============================================================================================ Cnn_AvgPooling
+struct sedb_cnn {
+    sedb_ctx* ctx = nullptr;
+    int n_blocks = 0, classes = 0;
+    std::vector<int> channels, pools;
+    int ratio = 1;                    // 2 ** num_pools (spectogram_models.py:167-172,200)
+    // block 0 conv1 (C_in = 1)
+    float* w_in = nullptr;            // [C0][9]
+    float* scale_in = nullptr;
+    float* shift_in = nullptr;
+    std::vector<UmmaLayer> layers;    // block0.conv2, block1.conv1, block1.conv2, ...
+    float* fc_w = nullptr;            // [classes][C_last]
+    float* fc_b = nullptr;
+    bool loaded = false;
+};
+
+struct CnnPlan {
+    std::vector<PlaneGeom> planes;            // planes[0] = output of block0.conv1, planes[i+1] = output of layers[i]
+    std::vector<sedb::ConvParams> params;     // per umma layer
+    size_t ws_bytes = 0;
+    int Hf = 0, Wf = 0;
+    unsigned long long tag = 0;
+};
+
+static int cnn_make_plan(const sedb_cnn* m, long long n_clips, long long T, CnnPlan& plan) {
+    const int nl = static_cast<int>(m->layers.size());
+    plan.planes.assign(nl + 1, PlaneGeom{});
+    plan.params.assign(nl, sedb::ConvParams{});
+    int H = static_cast<int>(T), W = SEDB_MEL_BINS;
+    plan.planes[0].C = m->channels[0];
+    plan.planes[0].H = H;
+    plan.planes[0].W = W;
+    for (int i = 0; i < nl; ++i) {
+        const UmmaLayer& L = m->layers[i];
+        const int S_in = plan_umma_layer(L, H, W, plan.params[i]);
+        if (S_in < 0) return fail("unsupported feature-map width %d", W);
+        plan.planes[i].S = S_in;
+        H = plan.params[i].Ho;
+        W = plan.params[i].Wo;
+        if (L.pool == 1) { H = plan.params[i].H; W = plan.params[i].W; }
+        if (H < 1 || W < 1) return fail("input of %lld frames is too short for this model's pooling", T);
+        plan.planes[i + 1].C = L.cout;
+        plan.planes[i + 1].H = H;
+        plan.planes[i + 1].W = W;
+    }
+    plan.planes[nl].S = final_plane_S(0, H, W);
+    plan.Hf = H;
+    plan.Wf = W;
+    size_t off = 128;                                   // header: geometry tag
+    unsigned long long tag = mix_tag(0x5EDBull, static_cast<unsigned long long>(n_clips));
+    tag = mix_tag(tag, static_cast<unsigned long long>(T));
+    for (auto& g : plan.planes) {
+        g.offset = off;
+        off += (g.bytes_per_img() * static_cast<size_t>(n_clips) + 127) / 128 * 128;
+        tag = mix_tag(tag, (static_cast<unsigned long long>(g.C) << 40) ^ (static_cast<unsigned long long>(g.S) << 8) ^ g.W);
+    }
+    plan.ws_bytes = off;
+    plan.tag = tag | 1ull;
+    return 0;
+}
+
+static int sedb_cnn_kernels_init() {
+    CUDA_TRY(cudaFuncSetAttribute(sedb::conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(sedb::conv_in1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    return 0;
+}
+
+extern "C" {
+
+int sedb_cnn_create(sedb_ctx_t* ctx, const int* channels, const int* pools, int n_blocks, int classes_num,
+                    sedb_cnn_t** out) {
+    if (!ctx || !channels || !pools || !out) return fail("sedb_cnn_create: null argument");
+    *out = nullptr;
+    if (n_blocks < 1 || n_blocks > 8 || classes_num < 1) return fail("sedb_cnn_create: bad model_config");
+    for (int i = 0; i < n_blocks; ++i) {
+        if (channels[i] % 16 || channels[i] < 16 || channels[i] > 1024)
+            return fail("sedb_cnn_create: channels[%d]=%d must be a multiple of 16 in [16,1024]", i, channels[i]);
+        if (channels[i] > 128 && channels[i] % 128)
+            return fail("sedb_cnn_create: channels[%d]=%d above 128 must be a multiple of 128", i, channels[i]);
+        if (pools[i] != 1 && pools[i] != 2) return fail("sedb_cnn_create: pool size must be 1 or 2");
+    }
+    sedb_cnn* m = new (std::nothrow) sedb_cnn();
+    if (!m) return fail("out of host memory");
+    m->ctx = ctx;
+    m->n_blocks = n_blocks;
+    m->classes = classes_num;
+    m->channels.assign(channels, channels + n_blocks);
+    m->pools.assign(pools, pools + n_blocks);
+    // spectogram_models.py:167-172: num_pools starts at 1 and counts pool==2 among blocks 1..n-1
+    int num_pools = 1;
+    for (int i = 1; i < n_blocks; ++i)
+        if (pools[i] == 2) ++num_pools;
+    m->ratio = 1 << num_pools;
+    const int C0 = channels[0];
+    CUDA_TRY(cudaMalloc(&m->w_in, C0 * 9 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&m->scale_in, C0 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&m->shift_in, C0 * sizeof(float)));
+    for (int b = 0; b < n_blocks; ++b) {
+        if (b > 0) {
+            UmmaLayer L;
+            L.cin = channels[b - 1];
+            L.cout = channels[b];
+            L.pool = 1;
+            if (int rc = alloc_layer_params(L)) return rc;
+            m->layers.push_back(L);
+        }
+        UmmaLayer L;
+        L.cin = channels[b];
+        L.cout = channels[b];
+        L.pool = pools[b];
+        if (int rc = alloc_layer_params(L)) return rc;
+        m->layers.push_back(L);
+    }
+    CUDA_TRY(cudaMalloc(&m->fc_w, static_cast<size_t>(classes_num) * channels[n_blocks - 1] * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&m->fc_b, classes_num * sizeof(float)));
+    *out = m;
+    return 0;
+}
+
+int sedb_cnn_destroy(sedb_cnn_t* m) {
+    if (!m) return 0;
+    cudaFree(m->w_in);
+    cudaFree(m->scale_in);
+    cudaFree(m->shift_in);
+    for (auto& L : m->layers) free_layer_params(L);
+    cudaFree(m->fc_w);
+    cudaFree(m->fc_b);
+    delete m;
+    return 0;
+}
+
+int sedb_cnn_load(sedb_cnn_t* m, const float* const* t, int n_tensors, void* stream) {
+    if (!m || !t) return fail("sedb_cnn_load: null argument");
+    if (n_tensors != 10 * m->n_blocks + 2)
+        return fail("sedb_cnn_load: expected %d tensors (10 per block + event_fc weight/bias), got %d",
+                    10 * m->n_blocks + 2, n_tensors);
+    for (int i = 0; i < n_tensors; ++i)
+        if (!t[i]) return fail("sedb_cnn_load: tensor %d is null", i);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int li = 0;
+    for (int b = 0; b < m->n_blocks; ++b) {
+        const float* const* q = t + 10 * b;   // conv1.w conv2.w bn1.{w,b,rm,rv} bn2.{w,b,rm,rv}
+        if (b == 0) {
+            CUDA_TRY(cudaMemcpyAsync(m->w_in, q[0], m->channels[0] * 9 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+            sedb::bn_fold_kernel<<<(m->channels[0] + 127) / 128, 128, 0, st>>>(q[2], q[3], q[4], q[5], nullptr, 1e-5f,
+                                                                             m->channels[0], m->scale_in, m->shift_in);
+            g_launches.fetch_add(1);
+        } else {
+            if (int rc = fold_and_pack(m->layers[li++], q[0], nullptr, q[2], q[3], q[4], q[5], st)) return rc;
+        }
+        if (int rc = fold_and_pack(m->layers[li++], q[1], nullptr, q[6], q[7], q[8], q[9], st)) return rc;
+    }
+    const int Cl = m->channels[m->n_blocks - 1];
+    CUDA_TRY(cudaMemcpyAsync(m->fc_w, t[10 * m->n_blocks], static_cast<size_t>(m->classes) * Cl * sizeof(float),
+                             cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(m->fc_b, t[10 * m->n_blocks + 1], m->classes * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaGetLastError());
+    m->loaded = true;
+    return 0;
+}
+
+long long sedb_cnn_out_frames(const sedb_cnn_t* m, long long T) {
+    if (!m) return -1;
+    long long H = T;
+    for (int b = 0; b < m->n_blocks; ++b) H /= m->pools[b];
+    return H * m->ratio;
+}
+
+size_t sedb_cnn_workspace_bytes(const sedb_cnn_t* m, long long n_clips, long long T) {
+    if (!m || n_clips <= 0 || T <= 0) return 0;
+    CnnPlan plan;
+    if (cnn_make_plan(m, n_clips, T, plan)) return 0;
+    return plan.ws_bytes;
+}
+
+int sedb_cnn_forward(sedb_cnn_t* m, const float* x_dev, long long n_clips, long long T, float* logits_dev,
+                     float* probs_dev, void* workspace_dev, size_t workspace_bytes, void* stream) {
+    if (!m || !x_dev || !workspace_dev) return fail("sedb_cnn_forward: null argument");
+    if (!logits_dev && !probs_dev) return fail("sedb_cnn_forward: no output requested");
+    if (!m->loaded) return fail("sedb_cnn_forward: parameters not loaded (call sedb_cnn_load)");
+    if (n_clips < 0 || T < 1 || n_clips > (1 << 20) || T > (1 << 20)) return fail("sedb_cnn_forward: bad shape");
+    if (n_clips == 0) return 0;
+    if (reinterpret_cast<uintptr_t>(workspace_dev) & 127) return fail("workspace must be 128-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CnnPlan plan;
+    if (int rc = cnn_make_plan(m, n_clips, T, plan)) return rc;
+    if (workspace_bytes < plan.ws_bytes)
+        return fail("sedb_cnn_forward: workspace has %zu bytes, needs %zu", workspace_bytes, plan.ws_bytes);
+    uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+    if (int rc = prepare_workspace(ws, plan.ws_bytes, plan.tag, st)) return rc;
+    const int n_img = static_cast<int>(n_clips);
+    {   // block 0 conv1
+        const PlaneGeom& g = plan.planes[0];
+        const long long total = static_cast<long long>(n_img) * g.H * g.W;
+        long long blocks = (total + 255) / 256;
+        if (blocks > 148LL * 16) blocks = 148LL * 16;
+        const size_t smem = static_cast<size_t>(g.C) * 11 * sizeof(float);
+        sedb::conv_in2d_kernel<<<static_cast<int>(blocks), 256, smem, st>>>(x_dev, m->w_in, m->scale_in, m->shift_in,
+                                                                           ws + g.offset, n_img, g.H, g.W, g.C, g.S);
+        g_launches.fetch_add(1);
+        CUDA_TRY(cudaGetLastError());
+    }
+    for (size_t i = 0; i < m->layers.size(); ++i) {
+        if (int rc = launch_umma_layer(m->ctx, m->layers[i], plan.params[i], ws + plan.planes[i].offset,
+                                       ws + plan.planes[i + 1].offset, n_img, plan.planes[i].S, plan.planes[i + 1].S, st))
+            return rc;
+    }
+    {
+        const PlaneGeom& g = plan.planes.back();
+        const long long warps = static_cast<long long>(n_img) * plan.Hf;
+        const int blocks = static_cast<int>((warps * 32 + 255) / 256);
+        sedb::head2d_kernel<<<blocks, 256, 0, st>>>(ws + g.offset, m->fc_w, m->fc_b, logits_dev, probs_dev, n_img, g.C,
+                                                   plan.Hf, plan.Wf, g.S, m->classes, m->ratio);
+        g_launches.fetch_add(1);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // extern "C"
+
+// CNN stage of the host pipelines: log-mel image resident in ctx->d_out -> probabilities -> host.
+static int sedb_cnn_forward_pipeline(sedb_ctx_t* c, sedb_cnn_t* cnn, long long n_clips, long long T, float* probs_host) {
+    const size_t need = sedb_cnn_workspace_bytes(cnn, n_clips, T);
+    if (need == 0) return fail("cannot plan the CNN for %lld clips x %lld frames", n_clips, T);
+    if (need > c->d_ws_bytes) {
+        cudaFree(c->d_ws);
+        c->d_ws = nullptr;
+        CUDA_TRY(cudaMalloc(&c->d_ws, need));
+        c->d_ws_bytes = need;
+    }
+    const size_t n_out = static_cast<size_t>(n_clips) * sedb_cnn_out_frames(cnn, T) * cnn->classes;
+    if (n_out > c->d_probs_elems) {
+        cudaFree(c->d_probs);
+        c->d_probs = nullptr;
+        CUDA_TRY(cudaMalloc(&c->d_probs, n_out * sizeof(float)));
+        c->d_probs_elems = n_out;
+    }
+    if (int rc = sedb_cnn_forward(cnn, c->d_out, n_clips, T, nullptr, c->d_probs, c->d_ws, c->d_ws_bytes, c->s_comp))
+        return rc;
+    CUDA_TRY(cudaMemcpyAsync(probs_host, c->d_probs, n_out * sizeof(float), cudaMemcpyDeviceToHost, c->s_comp));
+    return 0;
+}
+
+// ============================================================================================ M5
+struct sedb_m5 {
+    sedb_ctx* ctx = nullptr;
+    int classes = 0;
+    float* w_in = nullptr;            // conv_block1 conv: [64][79]
+    float* scale_in = nullptr;
+    float* shift_in = nullptr;
+    std::vector<UmmaLayer> layers;    // the 8 k=3 convolutions
+    float* fc_w = nullptr;            // [classes][256]
+    float* fc_b = nullptr;
+    bool loaded = false;
+};
+
+struct M5Plan {
+    std::vector<PlaneGeom> planes;
+    std::vector<sedb::ConvParams> params;
+    size_t ws_bytes = 0;
+    int Lf = 0;
+    unsigned long long tag = 0;
+};
+
+static const int kM5Cin[8] = {64, 64, 64, 64, 64, 128, 128, 256};
+static const int kM5Cout[8] = {64, 64, 64, 64, 128, 128, 256, 256};
+static const int kM5Pool[8] = {1, 4, 1, 4, 1, 4, 1, 1};          // waveform_models.py:22-56
+static const int kM5FrameLen = SEDB_FRAME_SIZE;                  // M5 input length (waveform_configs.frame_size)
+
+static int m5_make_plan(const sedb_m5* m, long long n_frames, M5Plan& plan) {
+    plan.planes.assign(9, PlaneGeom{});
+    plan.params.assign(8, sedb::ConvParams{});
+    int L = ((kM5FrameLen + 2 * 39 - 79) / 4 + 1) / 4;            // conv k79 s4 p39 -> 7920, MaxPool(4) -> 1980
+    plan.planes[0].C = 64;
+    plan.planes[0].H = 1;
+    plan.planes[0].W = L;
+    for (int i = 0; i < 8; ++i) {
+        const int S_in = plan_umma_layer(m->layers[i], 1, L, plan.params[i]);
+        if (S_in < 0) return fail("m5 planning failed");
+        plan.planes[i].S = S_in;
+        if (m->layers[i].pool != 1) L = plan.params[i].Wo;
+        plan.planes[i + 1].C = m->layers[i].cout;
+        plan.planes[i + 1].H = 1;
+        plan.planes[i + 1].W = L;
+    }
+    plan.planes[8].S = final_plane_S(1, 1, L);
+    plan.Lf = L;
+    size_t off = 128;
+    unsigned long long tag = mix_tag(0x35ull, static_cast<unsigned long long>(n_frames));
+    for (auto& g : plan.planes) {
+        g.offset = off;
+        off += (g.bytes_per_img() * static_cast<size_t>(n_frames) + 127) / 128 * 128;
+        tag = mix_tag(tag, (static_cast<unsigned long long>(g.C) << 40) ^ (static_cast<unsigned long long>(g.S) << 8) ^ g.W);
+    }
+    plan.ws_bytes = off;
+    plan.tag = tag | 1ull;
+    return 0;
+}
+
+extern "C" {
+
+int sedb_m5_create(sedb_ctx_t* ctx, int classes_num, sedb_m5_t** out) {
+    if (!ctx || !out) return fail("sedb_m5_create: null argument");
+    *out = nullptr;
+    if (classes_num < 1) return fail("sedb_m5_create: classes_num must be positive");
+    sedb_m5* m = new (std::nothrow) sedb_m5();
+    if (!m) return fail("out of host memory");
+    m->ctx = ctx;
+    m->classes = classes_num;
+    CUDA_TRY(cudaMalloc(&m->w_in, 64 * 80 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&m->scale_in, 64 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&m->shift_in, 64 * sizeof(float)));
+    for (int i = 0; i < 8; ++i) {
+        UmmaLayer L;
+        L.cin = kM5Cin[i];
+        L.cout = kM5Cout[i];
+        L.pool = kM5Pool[i];
+        L.mode = 1;
+        L.ntaps = 3;
+        if (int rc = alloc_layer_params(L)) return rc;
+        m->layers.push_back(L);
+    }
+    CUDA_TRY(cudaMalloc(&m->fc_w, static_cast<size_t>(classes_num) * 256 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&m->fc_b, classes_num * sizeof(float)));
+    *out = m;
+    return 0;
+}
+
+int sedb_m5_destroy(sedb_m5_t* m) {
+    if (!m) return 0;
+    cudaFree(m->w_in);
+    cudaFree(m->scale_in);
+    cudaFree(m->shift_in);
+    for (auto& L : m->layers) free_layer_params(L);
+    cudaFree(m->fc_w);
+    cudaFree(m->fc_b);
+    delete m;
+    return 0;
+}
+
+int sedb_m5_load(sedb_m5_t* m, const float* const* t, int n_tensors, void* stream) {
+    if (!m || !t) return fail("sedb_m5_load: null argument");
+    if (n_tensors != 9 * 6 + 2) return fail("sedb_m5_load: expected 56 tensors (6 per conv+bn pair, fc weight/bias), got %d", n_tensors);
+    for (int i = 0; i < n_tensors; ++i)
+        if (!t[i]) return fail("sedb_m5_load: tensor %d is null", i);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // pair 0: conv_block1 (k=79): conv.w conv.b bn.w bn.b bn.rm bn.rv
+    CUDA_TRY(cudaMemcpyAsync(m->w_in, t[0], 64 * 79 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    sedb::bn_fold_kernel<<<1, 128, 0, st>>>(t[2], t[3], t[4], t[5], t[1], 1e-5f, 64, m->scale_in, m->shift_in);
+    g_launches.fetch_add(1);
+    for (int i = 0; i < 8; ++i) {
+        const float* const* q = t + 6 * (i + 1);
+        if (int rc = fold_and_pack(m->layers[i], q[0], q[1], q[2], q[3], q[4], q[5], st)) return rc;
+    }
+    CUDA_TRY(cudaMemcpyAsync(m->fc_w, t[54], static_cast<size_t>(m->classes) * 256 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(m->fc_b, t[55], m->classes * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    CUDA_TRY(cudaGetLastError());
+    m->loaded = true;
+    return 0;
+}
+
+size_t sedb_m5_workspace_bytes(const sedb_m5_t* m, long long n_frames) {
+    if (!m || n_frames <= 0) return 0;
+    M5Plan plan;
+    if (m5_make_plan(m, n_frames, plan)) return 0;
+    return plan.ws_bytes;
+}
+
+int sedb_m5_forward(sedb_m5_t* m, const float* x_dev, long long n_frames, float* logits_dev, void* workspace_dev,
+                    size_t workspace_bytes, void* stream) {
+    if (!m || !x_dev || !logits_dev || !workspace_dev) return fail("sedb_m5_forward: null argument");
+    if (!m->loaded) return fail("sedb_m5_forward: parameters not loaded (call sedb_m5_load)");
+    if (n_frames < 0 || n_frames > (1 << 24)) return fail("sedb_m5_forward: bad frame count");
+    if (n_frames == 0) return 0;
+    if (reinterpret_cast<uintptr_t>(workspace_dev) & 127) return fail("workspace must be 128-byte aligned");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    M5Plan plan;
+    if (int rc = m5_make_plan(m, n_frames, plan)) return rc;
+    if (workspace_bytes < plan.ws_bytes)
+        return fail("sedb_m5_forward: workspace has %zu bytes, needs %zu", workspace_bytes, plan.ws_bytes);
+    uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
+    if (int rc = prepare_workspace(ws, plan.ws_bytes, plan.tag, st)) return rc;
+    const int n = static_cast<int>(n_frames);
+    {
+        const PlaneGeom& g = plan.planes[0];
+        const int tiles = (g.W + sedb::kIn1dTile - 1) / sedb::kIn1dTile;
+        dim3 grid(tiles, n);
+        sedb::conv_in1d_kernel<<<grid, 256, sedb::kIn1dSmem, st>>>(x_dev, m->w_in, m->scale_in, m->shift_in, ws + g.offset,
+                                                                  kM5FrameLen, g.W, g.S);
+        g_launches.fetch_add(1);
+        CUDA_TRY(cudaGetLastError());
+    }
+    for (int i = 0; i < 8; ++i) {
+        if (int rc = launch_umma_layer(m->ctx, m->layers[i], plan.params[i], ws + plan.planes[i].offset,
+                                       ws + plan.planes[i + 1].offset, n, plan.planes[i].S, plan.planes[i + 1].S, st))
+            return rc;
+    }
+    {
+        const PlaneGeom& g = plan.planes[8];
+        const int blocks = (n * 32 + 255) / 256;
+        sedb::head1d_kernel<<<blocks, 256, 0, st>>>(ws + g.offset, m->fc_w, m->fc_b, logits_dev, n, g.C, plan.Lf, g.S,
+                                                   m->classes);
+        g_launches.fetch_add(1);
+        CUDA_TRY(cudaGetLastError());
+    }
+    return 0;
+}
+
+}  // extern "C"

@@ -52,6 +52,11 @@ def _as_cuda_f32(x) -> torch.Tensor:
     return torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).cuda()
 
 
+def _row_stride(w) -> int:
+    # torch reports an arbitrary stride for a size-1 leading dimension
+    return w.stride(0) if w.shape[0] > 1 else max(w.stride(0), w.shape[1])
+
+
 def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -80,7 +85,7 @@ def waveform_to_log_mel(wave, mean=None, std=None) -> torch.Tensor:
     norm = _norm_tensor(mean, std)
     out = torch.empty((B, num_frames(n), cfg.mel_bins), dtype=torch.float32, device=w.device)
     with torch.cuda.device(w.device):
-        _ext.check(_ext.load().sedb_logmel_f32(_ext.context(), _ptr(w), B, n, w.stride(0), _ptr(norm), _ptr(out),
+        _ext.check(_ext.load().sedb_logmel_f32(_ext.context(), _ptr(w), B, n, _row_stride(w), _ptr(norm), _ptr(out),
                                                _ext.stream_ptr()))
     return out[0] if squeeze else out
 
@@ -94,7 +99,7 @@ def multichannel_stft(multichannel_signal):
     C, n = w.shape
     spec = torch.empty((C, num_frames(n), NUM_BINS), dtype=torch.complex64, device=w.device)
     with torch.cuda.device(w.device):
-        _ext.check(_ext.load().sedb_stft_c64(_ext.context(), _ptr(w), C, n, w.stride(0), _ptr(spec),
+        _ext.check(_ext.load().sedb_stft_c64(_ext.context(), _ptr(w), C, n, _row_stride(w), _ptr(spec),
                                              _ext.stream_ptr()))
     return spec.cpu().numpy() if is_np else spec
 

@@ -1,0 +1,67 @@
+"""Shared plumbing of the drop-in nn.Modules: native handle lifetime, parameter repacking, workspaces."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from .. import _ext
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class NativeHandle:
+    """Owns a sedb_cnn_t / sedb_m5_t for one CUDA device and keeps it in sync with the module's tensors."""
+
+    def __init__(self, create, destroy, load):
+        self._create, self._destroy, self._load = create, destroy, load
+        self._handles = {}       # device index -> (handle, parameter fingerprint)
+        self._workspaces = {}    # (device, key) -> uint8 tensor
+
+    def get(self, device: torch.device, tensors):
+        """Returns the handle for `device`, (re)loading parameters when any tensor changed since the last call."""
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        fp = tuple((t.data_ptr(), t._version) for t in tensors)
+        entry = self._handles.get(idx)
+        if entry is None:
+            h = ctypes.c_void_p()
+            self._create(ctypes.byref(h))
+            entry = [h, None]
+            self._handles[idx] = entry
+        if entry[1] != fp:
+            prepared = [t.detach().to(device=device, dtype=torch.float32).contiguous() for t in tensors]
+            arr = (ctypes.c_void_p * len(prepared))(*[t.data_ptr() for t in prepared])
+            self._load(entry[0], arr, len(prepared))
+            torch.cuda.current_stream(device).synchronize()      # `prepared` temporaries may be freed after this
+            entry[1] = fp
+        return entry[0]
+
+    def workspace(self, device: torch.device, key, nbytes: int) -> torch.Tensor:
+        k = (device.index, key)
+        ws = self._workspaces.get(k)
+        if ws is None or ws.numel() < nbytes:
+            self._workspaces.clear()                             # keep at most one live workspace per module
+            ws = torch.empty(nbytes + 128, dtype=torch.uint8, device=device)
+            self._workspaces[k] = ws
+        return ws
+
+    def close(self):
+        for h, _ in self._handles.values():
+            try:
+                self._destroy(h)
+            except Exception:
+                pass
+        self._handles.clear()
+        self._workspaces.clear()
+
+    def __del__(self):
+        self.close()
+
+
+def aligned_ptr(ws: torch.Tensor):
+    """128-byte aligned address inside a uint8 workspace tensor and the bytes left behind it."""
+    base = ws.data_ptr()
+    off = (-base) % 128
+    return ctypes.c_void_p(base + off), ws.numel() - off

@@ -36,6 +36,9 @@ if "--skip-probe" not in sys.argv:
                     res[key] = "EXC " + repr(e)
                 print(key, res[key], flush=True)
 
+if "--probe-only" in sys.argv:
+    json.dump(res, open(os.path.join(ROOT, "gpurun_out", "probe.json"), "w"), indent=1) if os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True) is None else None
+    sys.exit(0)
 # ---- logmel parity
 def logmel_err(name, y):
     ref = R.waveform_to_log_mel(y)
