@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- audio-hours/sec of the SED hot path (fused log-mel + Cnn_AvgPooling frame probabilities) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--clips C] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic TAU-SED-2019-shaped clips (60 s, 48 kHz, mono):
+waveform [C, 2 880 000] f32 -> fused framing+Hann+DFT+mel+dB (tcgen05) -> per-mel-bin normalisation -> Cnn_AvgPooling
+(main.py:35 config 32-64-128-128) -> frame probabilities [C, 176, 1].  Clips are independent units: with N GPUs every
+rank processes its own C clips (weak scaling, no data-path collective); `value` is the whole-job aggregate.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract:
+  roofline      dominant kernel (logmel_fused_kernel): algorithmic HBM bytes / CUDA-event time vs MEASURED_PEAKS.json
+  tensor        executed tensor-core FLOPs of the same kernel vs the measured bf16 peak (it is tensor-bound in practice)
+  cpu_baseline  the oracle port of the reference CPU path timed on this box's host cores on a bounded sample
+  e2e           same metric through the C-ABI host-buffer entry point (pinned host memory, H2D + D2H inside the timing)
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+CLIP_SAMPLES = 2_880_000          # 60 s x 48 kHz
+CLIP_SECONDS = 60.0
+FRAMES = 182                      # 1 + 2 880 000 // 15 840
+ALGO_BYTES_PER_CLIP = 11_566_592  # 11 520 000 read + 46 592 written
+CNN_FLOP_PER_CLIP = 965_768_704
+# executed tensor FLOPs of the fused log-mel kernel per frame: stage 1 (2 x 128x128x256) + stage 2 (4 x 128x128x128)
+# MACs, x3 split products, x2 FLOP/MAC
+LOGMEL_MMA_FLOP_PER_FRAME = (2 * 128 * 128 * 256 + 4 * 128 * 128 * 128) * 3 * 2
+METRIC = "audio-hours/sec (log-mel + CNN frame SED)"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "measured"
+        except Exception:
+            pass
+    return 6650.0, 1400.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
+
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def stop(self):
+        self._stop.set()
+        self.join(timeout=3)
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------- CPU baseline
+def _cpu_logmel_clip(seed):
+    """Reference formulation of dataset/spectogram/preprocess.py:21-45 on one synthetic clip (oracle port)."""
+    import numpy as np
+    from oracle import logmel_ref
+    import signals
+    y = signals.white(CLIP_SAMPLES, seed)
+    spec = logmel_ref.multichannel_stft(y[:, None])                    # float64 rFFT per frame -> complex64
+    power = np.abs(spec) ** 2                                           # float32
+    mel = np.dot(power, logmel_ref.mel_filter_bank_matrix())            # the reference's 3-D x 2-D np.dot
+    return logmel_ref.power_to_db(mel).astype(np.float32)[0]
+
+
+def cpu_reference_pass(n_clips, workers):
+    """Oracle port of the whole path on the host: log-mel per clip (process pool) + Cnn_AvgPooling on torch CPU."""
+    import multiprocessing as mp
+    import numpy as np
+    import torch
+    from oracle import cnn_ref
+    import refmodels
+    t0 = time.perf_counter()
+    if workers > 1:
+        with mp.get_context("fork").Pool(workers) as pool:
+            lms = pool.map(_cpu_logmel_clip, range(n_clips))
+    else:
+        lms = [_cpu_logmel_clip(i) for i in range(n_clips)]
+    lm = np.stack(lms)
+    mean, std = lm.mean((0, 1)), lm.std((0, 1))
+    _, sd = refmodels.seeded_cnn(refmodels.MAIN_CFG)
+    x = torch.from_numpy(((lm - mean) / std)[:, None].astype(np.float32))
+    with torch.no_grad():
+        probs = torch.sigmoid(cnn_ref.cnn_avgpooling_forward(sd, x, [2, 2, 2, 1]))
+    dt = time.perf_counter() - t0
+    return dt, tuple(probs.shape)
+
+
+def cpu_baseline(n_clips=None):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    if n_clips is None:
+        n_clips = max(8, min(64, 2 * cores))
+    workers = min(cores, n_clips)
+    cpu_reference_pass(min(2, n_clips), min(2, workers))               # warm caches / imports
+    dt, _ = cpu_reference_pass(n_clips, workers)
+    return {"value": n_clips * CLIP_SECONDS / 3600.0 / dt, "unit": "audio-hours/sec", "cores": workers,
+            "kind": "port",
+            "sample": f"{n_clips} x 60 s clips: oracle log-mel (per-frame float64 rFFT, 3-D np.dot mel, dB) in a "
+                      f"{workers}-process pool + reference Cnn_AvgPooling(32-64-128-128) eval on torch CPU "
+                      f"({cores} threads); {dt:.2f} s"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port) on this box's host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    n_clips = max(8, min(32, cores))
+    workers = min(cores, n_clips)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_pass(min(2, n_clips), min(2, workers))
+    t = []
+    steps = max(1, min(args.steps, 5))
+    for _ in range(steps):
+        dt, _ = cpu_reference_pass(n_clips, workers)
+        t.append(dt)
+    per_step = sum(t) / len(t)
+    value = n_clips * CLIP_SECONDS / 3600.0 / per_step
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "audio-hours/sec", "n_gpus": args.gpus,
+            "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": per_step * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32", "data": "synthetic",
+            "config": {"workload": f"{n_clips} x 60 s TAU-SED-2019-shaped clips per step (bounded sample of the "
+                                   f"{args.clips}-clip GPU workload): log-mel + Cnn_AvgPooling(32-64-128-128) frame "
+                                   f"probabilities on host CPU"},
+            "cpu_baseline": {"value": value, "unit": "audio-hours/sec", "cores": workers, "kind": "port",
+                             "sample": f"{n_clips} clips/step, {workers} processes + {cores} torch threads"},
+            "e2e": {"value": value, "unit": "audio-hours/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import sed_b200  # noqa: F401
+    from sed_b200 import _ext, parallel
+    from sed_b200.dataset.spectogram import preprocess as P
+    import refmodels
+
+    rank, local_rank, world = parallel.init_process_group("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _ext.load()
+    C = args.clips
+
+    # synthetic inputs, resident in HBM before the timed region (2.95 GB per rank at C=256: far larger than L2)
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    wave = torch.empty(C, CLIP_SAMPLES, device=dev, dtype=torch.float32)
+    for i in range(C):
+        wave[i] = (torch.randn(CLIP_SAMPLES, device=dev, generator=g) * 0.1).clamp_(-1, 1)
+    model, _ = refmodels.seeded_cnn(refmodels.MAIN_CFG)
+    model = model.to(dev)
+    mean = torch.full((64,), 18.0, device=dev)
+    std = torch.full((64,), 6.0, device=dev)
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    lm_t, cnn_t = [], []
+
+    def step(record):
+        e0, e1, e2 = ev(), ev(), ev()
+        e0.record()
+        x = P.waveform_to_log_mel(wave, mean=mean, std=std)
+        e1.record()
+        probs = model.logits(x[:, None])
+        e2.record()
+        if record:
+            lm_t.append((e0, e1))
+            cnn_t.append((e1, e2))
+        return probs
+
+    for _ in range(args.warmup):
+        step(False)
+    torch.cuda.synchronize()
+    parallel.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = lib.sedb_launch_count()
+    t0, t1 = ev(), ev()
+    torch.cuda.synchronize()
+    t0.record()
+    for _ in range(args.steps):
+        probs = step(True)
+    t1.record()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    launches = lib.sedb_launch_count() - launches0
+    clocks = sampler.stop()
+    ms_total = parallel.max_over_ranks(t0.elapsed_time(t1), dev)
+    ms_step = ms_total / args.steps
+    lm_ms = sum(a.elapsed_time(b) for a, b in lm_t) / len(lm_t)
+    cnn_ms = sum(a.elapsed_time(b) for a, b in cnn_t) / len(cnn_t)
+    assert probs.shape == (C, 176, 1) and bool(torch.isfinite(probs).all())
+    value = world * C * CLIP_SECONDS / 3600.0 / (ms_step * 1e-3)
+
+    # ---- end to end through the C-ABI host-buffer entry point (pinned host memory, H2D + D2H in the timed region)
+    e2e_steps = max(1, min(args.steps, 5))
+    Ce = min(C, args.e2e_clips)
+    host_wave = torch.empty(Ce, CLIP_SAMPLES, dtype=torch.float32).pin_memory()
+    host_wave.copy_(wave[:Ce])
+    host_probs = torch.empty(Ce, 176, 1, dtype=torch.float32).pin_memory()
+    host_norm = torch.cat([mean, std]).cpu().pin_memory()
+    handle = model._native.get(dev, model._native_tensors())
+
+    def e2e_step():
+        _ext.check(lib.sedb_sed_host_f32(_ext.context(), handle, ctypes.c_void_p(host_wave.data_ptr()), Ce,
+                                         CLIP_SAMPLES, CLIP_SAMPLES, ctypes.c_void_p(host_norm.data_ptr()),
+                                         ctypes.c_void_p(host_probs.data_ptr())))
+
+    e2e_step()
+    torch.cuda.synchronize()
+    parallel.barrier()
+    w0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()                                   # synchronises internally (result is on the host)
+    e2e_ms = parallel.max_over_ranks((time.perf_counter() - w0) * 1e3 / e2e_steps, dev)
+    e2e_ok = bool(torch.allclose(host_probs, probs[:Ce].cpu(), atol=1e-4))
+    e2e_value = world * Ce * CLIP_SECONDS / 3600.0 / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        return
+    hbm_peak, tf_peak, src = measured_peaks()
+    achieved = C * ALGO_BYTES_PER_CLIP / (lm_ms * 1e-3) / 1e9
+    tflops = C * FRAMES * LOGMEL_MMA_FLOP_PER_FRAME / (lm_ms * 1e-3) / 1e12
+    line = {
+        "metric": METRIC, "value": value, "unit": "audio-hours/sec", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16x3-split (fp32 accumulate)" if not lib.sedb_split_is_fp16() else
+        "fp16x3-split (fp32 accumulate)", "data": "synthetic",
+        "config": {"workload": f"{C} x 60 s TAU-SED-2019-shaped clips per GPU: fused log-mel (win 31680, hop 15840, "
+                               f"NFFT 32768, 64 mel) + Cnn_AvgPooling(32-64-128-128) frame probabilities",
+                   "clips_per_gpu": C, "l2_policy": "inputs (2.95 GB/GPU) larger than L2",
+                   "stage_ms": {"logmel": lm_ms, "cnn": cnn_ms}},
+        "roofline": {"kernel": "logmel_fused_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": None, "peak_source": src,
+                     "algorithmic_bytes_per_launch": C * ALGO_BYTES_PER_CLIP, "ms_per_launch": lm_ms},
+        "tensor": {"kernel": "logmel_fused_kernel", "executed_tflops": tflops, "peak": tf_peak, "unit": "TFLOP/s",
+                   "frac": tflops / tf_peak, "note": "split-operand DFT GEMMs; the kernel is tensor-bound in practice"},
+        "cnn": {"ms": cnn_ms, "algorithmic_tflops": C * CNN_FLOP_PER_CLIP / (cnn_ms * 1e-3) / 1e12},
+        "e2e": {"value": e2e_value, "unit": "audio-hours/sec", "h2d_bytes_per_step": Ce * CLIP_SAMPLES * 4 + 512,
+                "d2h_bytes_per_step": Ce * 176 * 4, "ms_per_step": e2e_ms, "clips_per_step": Ce,
+                "matches_device_path": e2e_ok},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--clips", type=int, default=256, help="60 s clips per GPU per step")
+    ap.add_argument("--e2e-clips", type=int, default=256)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+    try:
+        import torch.distributed as dist
+        if dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == "__main__":
+    main()

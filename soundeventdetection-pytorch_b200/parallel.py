@@ -1,0 +1,83 @@
+"""Multi-GPU plumbing for the inference path: clips (or M5 frames) are independent units, so they are split
+contiguously across ranks -- one process per GPU -- with no collective on the data path.
+`torch.distributed` is used only for rendezvous, the timing reduction (max over ranks) and an optional gather of the
+per-rank results on the host.
+"""
+from __future__ import annotations
+
+import os
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_range(n_items: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """Contiguous [start, stop) of `n_items` owned by `rank`; the remainder goes to the lowest ranks."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError(f"bad rank/world_size {rank}/{world_size}")
+    if n_items < 0:
+        raise ValueError("n_items must be non-negative")
+    base, rem = divmod(n_items, world_size)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def env_rank_world() -> Tuple[int, int, int]:
+    """(rank, local_rank, world_size) from the torchrun environment (1-process defaults)."""
+    return (int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")),
+            int(os.environ.get("WORLD_SIZE", "1")))
+
+
+def init_process_group(backend: str | None = None) -> Tuple[int, int, int]:
+    rank, local_rank, world = env_rank_world()
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = "nccl" if torch.cuda.is_available() else "gloo"
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29500")
+        if backend == "nccl":
+            torch.cuda.set_device(local_rank)
+        dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, local_rank, world
+
+
+def barrier():
+    if dist.is_initialized():
+        dist.barrier()
+
+
+def max_over_ranks(value: float, device=None) -> float:
+    """Largest `value` over all ranks (timing reduction); identity without a process group."""
+    if not dist.is_initialized():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, device=None) -> float:
+    if not dist.is_initialized():
+        return float(value)
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def gather_sharded(local: torch.Tensor, n_items: int) -> torch.Tensor | None:
+    """Reassembles per-rank result shards (split with `shard_range` along dim 0) on rank 0; None elsewhere."""
+    if not dist.is_initialized():
+        return local
+    world, rank = dist.get_world_size(), dist.get_rank()
+    longest = max(shard_range(n_items, r, world)[1] - shard_range(n_items, r, world)[0] for r in range(world))
+    padded = torch.zeros((longest,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    padded[: local.shape[0]] = local
+    bufs = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(bufs, padded)
+    if rank != 0:
+        return None
+    parts = []
+    for r in range(world):
+        a, b = shard_range(n_items, r, world)
+        parts.append(bufs[r][: b - a])
+    return torch.cat(parts, dim=0)

@@ -91,11 +91,11 @@ def main():
     assert list(sd_ref.keys()) == list(sd_ours.keys())
     for k in sd_ref:
         assert torch.equal(sd_ref[k], sd_ours[k]), f"seeded init differs at {k}"
-    sd = cnn_ref.randomize_bn_({k: v.clone() for k, v in sd_ref.items()}, seed=11)
+    import refmodels
+    sd = refmodels.m5_test_weights(sd_ref, 11)
     ref.load_state_dict(sd)
     ref.eval()
-    g = torch.Generator().manual_seed(5)
-    x = torch.randn(6, 1, 31680, generator=g) * 0.1
+    x = refmodels.m5_inputs(10)
     with torch.no_grad():
         y_ref = ref(x)
         y_or = cnn_ref.m5_forward(sd, x)

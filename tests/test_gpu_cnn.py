@@ -1,0 +1,143 @@
+"""GPU parity of the CNN paths (Cnn_AvgPooling, M5) against the reference-module goldens and the CPU oracle.
+Tolerances (north star): frame probabilities within 1e-3; utils/metric_utils results identical."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import sed_b200
+from sed_b200 import _ext
+from sed_b200.dataset.spectogram import preprocess as P
+from oracle import cnn_ref, logmel_ref, metrics_ref
+import refmodels
+import signals
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TOL_PROB = 1e-3
+
+
+@pytest.mark.parametrize("cfg_name,cfg,Ts", [("main", refmodels.MAIN_CFG, (30, 181, 182, 183, 184)),
+                                             ("default", refmodels.DEFAULT_CFG, (30, 182))])
+def test_cnn_vs_reference_golden(cfg_name, cfg, Ts):
+    gold = np.load(os.path.join(GOLD, "cnn_reference.npz"))
+    m, _ = refmodels.seeded_cnn(cfg)
+    m = m.cuda()
+    for T in Ts:
+        x = refmodels.cnn_inputs(T, 100 + T).cuda()
+        y = m(x).cpu().numpy()
+        p = m.logits(x).cpu().numpy()
+        assert y.shape == gold[f"{cfg_name}_T{T}_logits"].shape
+        assert np.abs(p - gold[f"{cfg_name}_T{T}_probs"]).max() < TOL_PROB
+        assert np.abs(y - gold[f"{cfg_name}_T{T}_logits"]).max() < 2e-3
+
+
+@pytest.mark.parametrize("B,T", [(1, 8), (3, 61), (17, 182), (5, 9)])
+def test_cnn_vs_oracle_shapes(B, T):
+    m, sd = refmodels.seeded_cnn(refmodels.MAIN_CFG, seed=2, bn_seed=3)
+    m = m.cuda()
+    x = refmodels.cnn_inputs(T, B * 1000 + T, batch=B)
+    with torch.no_grad():
+        ref = torch.sigmoid(cnn_ref.cnn_avgpooling_forward(sd, x, [2, 2, 2, 1])).numpy()
+    p = m.logits(x.cuda()).cpu().numpy()
+    assert p.shape == ref.shape
+    assert np.abs(p - ref).max() < TOL_PROB
+
+
+def test_cnn_metrics_identical():
+    """calculate_metrics (21-threshold PR sweep, AP, F1) on both sides' probabilities must be identical."""
+    m, sd = refmodels.seeded_cnn(refmodels.MAIN_CFG)
+    m = m.cuda()
+    # give the head enough gain that probabilities spread over the thresholds
+    with torch.no_grad():
+        m.event_fc.weight.mul_(25.0)
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    ys = np.stack([signals.hdr(2880000, 30 + i) for i in range(2)])
+    lm = logmel_ref.waveform_to_log_mel(ys)
+    mean, std = lm.mean((0, 1)), lm.std((0, 1))
+    x_ref = torch.from_numpy(((lm - mean) / std)[:, None].astype(np.float32))
+    with torch.no_grad():
+        p_ref = torch.sigmoid(cnn_ref.cnn_avgpooling_forward(sd, x_ref, [2, 2, 2, 1])).numpy()
+    x_gpu = P.waveform_to_log_mel(torch.from_numpy(ys).float().cuda(), mean=mean, std=std)[:, None]
+    p_gpu = m.logits(x_gpu).cpu().numpy()
+    assert p_gpu.shape == (2, 176, 1)
+    assert np.abs(p_gpu - p_ref).max() < TOL_PROB
+    assert p_ref.max() - p_ref.min() > 0.3
+    rng = np.random.default_rng(0)
+    for i in range(2):
+        starts = sorted(rng.uniform(1, 55, size=3))
+        tgt = metrics_ref.create_event_matrix(182, starts, [s + 0.66 for s in starts])
+        r0, p0, ap0 = metrics_ref.calculate_metrics(p_ref[i], tgt)
+        r1, p1, ap1 = metrics_ref.calculate_metrics(p_gpu[i], tgt)
+        assert np.array_equal(r0, r1) and np.array_equal(p0, p1) and ap0 == ap1
+        assert metrics_ref.f_score(r0, p0)[10] == metrics_ref.f_score(r1, p1)[10]       # F1 at th = 0.5
+
+
+def test_cnn_repacks_after_parameter_change_and_state_dict_roundtrip():
+    m, sd = refmodels.seeded_cnn(refmodels.MAIN_CFG)
+    m = m.cuda()
+    x = refmodels.cnn_inputs(30, 5).cuda()
+    y0 = m(x).clone()
+    with torch.no_grad():
+        m.event_fc.bias.add_(1.0)
+    y1 = m(x)
+    assert torch.allclose(y1, y0 + 1.0, atol=1e-5)
+    m2, _ = refmodels.seeded_cnn(refmodels.MAIN_CFG, seed=9, bn_seed=9)
+    m2 = m2.cuda()
+    m2.load_state_dict(m.state_dict())
+    assert torch.equal(m2(x), y1)
+    assert m(x[:0]).shape == (0, 24, 1)
+
+
+def test_cnn_batch_independence_full_size():
+    """Config-3 sized batch: a clip's result does not depend on its neighbours or on the band/CTA schedule."""
+    m, _ = refmodels.seeded_cnn(refmodels.MAIN_CFG)
+    m = m.cuda()
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.randn(128, 1, 182, 64, device="cuda", generator=g)
+    p = m.logits(x)
+    assert p.shape == (128, 176, 1) and bool(torch.isfinite(p).all())
+    assert torch.equal(m.logits(x[77:78])[0], p[77])
+    # x8 frame repeat (interpolate)
+    assert torch.equal(p[:, 0::8], p[:, 7::8])
+
+
+def test_m5_vs_reference_golden_and_oracle():
+    gold = np.load(os.path.join(GOLD, "m5_reference.npz"))["logits"]
+    m, sd = refmodels.seeded_m5()
+    m = m.cuda()
+    y = m(refmodels.m5_inputs(10).cuda()).cpu().numpy()
+    assert y.shape == gold.shape
+    assert np.abs(y - gold).max() < 2e-3
+    assert np.abs(1 / (1 + np.exp(-y)) - 1 / (1 + np.exp(-gold))).max() < TOL_PROB
+    x = refmodels.m5_inputs(37, seed=3)
+    with torch.no_grad():
+        ref = cnn_ref.m5_forward(sd, x).numpy()
+    out = m(x.cuda()).cpu().numpy()
+    assert np.abs(out - ref).max() < 2e-3
+
+
+def test_end_to_end_host_entry_point():
+    """sedb_sed_host_f32: host waveforms -> log-mel -> CNN -> probabilities, against the oracle chain."""
+    lib = _ext.load()
+    m, sd = refmodels.seeded_cnn(refmodels.MAIN_CFG)
+    m = m.cuda()
+    ys = np.stack([signals.hdr(480000, 40 + i) for i in range(3)]).astype(np.float32)
+    mean = np.full(64, -10.0, dtype=np.float32)
+    std = np.full(64, 15.0, dtype=np.float32)
+    x0 = torch.zeros(1, 1, 31, 64, device="cuda")
+    m(x0)                                                   # creates + loads the native handle
+    handle = m._native.get(x0.device, m._native_tensors())
+    wave = torch.from_numpy(ys).pin_memory()
+    norm = torch.from_numpy(np.concatenate([mean, std])).pin_memory()
+    probs = torch.empty(3, 24, 1).pin_memory()
+    _ext.check(lib.sedb_sed_host_f32(_ext.context(), handle, ctypes.c_void_p(wave.data_ptr()), 3, 480000, 480000,
+                                     ctypes.c_void_p(norm.data_ptr()), ctypes.c_void_p(probs.data_ptr())))
+    lm = (logmel_ref.waveform_to_log_mel(ys.astype(np.float64)) - mean) / std
+    with torch.no_grad():
+        ref = torch.sigmoid(cnn_ref.cnn_avgpooling_forward(sd, torch.from_numpy(lm[:, None].astype(np.float32)),
+                                                           [2, 2, 2, 1])).numpy()
+    assert np.abs(probs.numpy() - ref).max() < TOL_PROB

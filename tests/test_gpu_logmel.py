@@ -1,0 +1,136 @@
+"""GPU parity of the log-mel path (through the C ABI via the ctypes shim) against the CPU oracle.
+Tolerance (north star): log-mel within 1e-2 dB max-abs of the reference CPU path."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import sed_b200
+from sed_b200 import _ext
+from sed_b200.dataset.spectogram import preprocess as P
+from oracle import logmel_ref as R
+import signals
+
+TOL_DB = 1e-2
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def gpu_logmel(y, **kw):
+    return P.waveform_to_log_mel(torch.from_numpy(np.asarray(y, dtype=np.float32)).cuda(), **kw).cpu().numpy()
+
+
+@pytest.mark.parametrize("N,K,am,bm,pad,neg", [(128, 16, 0, 0, 0, 0), (128, 64, 0, 1, 0, 0), (256, 64, 0, 0, 0, 0),
+                                               (128, 32, 0, 1, 16, 0), (64, 32, 1, 0, 0, 0), (32, 48, 0, 0, 0, 1)])
+def test_umma_descriptor_conventions(N, K, am, bm, pad, neg):
+    """Pins the tcgen05 shared-memory descriptor conventions the kernels rely on (see csrc/umma.cuh)."""
+    g = torch.Generator().manual_seed(N + K)
+    a = torch.randn(128, K, generator=g).cuda()
+    b = torch.randn(K, N, generator=g).cuda()
+    d = torch.zeros(128, N, device="cuda")
+    _ext.check(_ext.load().sedb_debug_umma_probe(ctypes.c_void_p(a.data_ptr()), ctypes.c_void_p(b.data_ptr()),
+                                                 ctypes.c_void_p(d.data_ptr()), N, K, am, bm, pad, neg, 0, None))
+    torch.cuda.synchronize()
+    ref = a.bfloat16().float() @ b.bfloat16().float()
+    if neg:
+        ref = -ref
+    assert (d - ref).abs().max() / ref.abs().max() < 1e-5
+
+
+@pytest.mark.parametrize("name", ["white", "hdr", "silence"])
+@pytest.mark.parametrize("n", [31680, 480000])
+def test_logmel_parity_signal_classes(name, n):
+    y = signals.ALL[name](n, 0)
+    out, ref = gpu_logmel(y), R.waveform_to_log_mel(y)
+    assert out.shape == ref.shape == (1 + n // 15840, 64) and out.dtype == np.float32
+    assert np.abs(out - ref).max() < TOL_DB
+
+
+@pytest.mark.parametrize("n", [2880000, 2880001, 16385, 47519, 47520])
+def test_logmel_parity_lengths(n):
+    """TAU-shaped 60 s clip, an unaligned length (scalar-load path), the shortest legal clip, frame-count edges."""
+    y = signals.hdr(n, 1)
+    out, ref = gpu_logmel(y), R.waveform_to_log_mel(y)
+    assert out.shape == ref.shape
+    assert np.abs(out - ref).max() < TOL_DB
+
+
+def test_logmel_golden_vectors():
+    gold = np.load(os.path.join(GOLD, "logmel_oracle.npz"))
+    for name, fn in signals.ALL.items():
+        assert np.abs(gpu_logmel(fn(100000, 3)) - gold[f"{name}_100000"]).max() < TOL_DB
+    assert np.abs(gpu_logmel(signals.tone(48000)) - gold["tone1k_48000"]).max() < TOL_DB
+    # impulse at sample 0 exercises the reflect padding; frames without energy sit on the 1e-10 floor (-100 dB)
+    out = gpu_logmel(signals.impulse(31680, 0))
+    g = gold["impulse0_31680"]
+    live = g > -99.0
+    assert np.abs(out - g)[live].max() < TOL_DB
+    assert np.all(out[~live] < -90.0)
+
+
+def test_logmel_batch_strided_and_normalised():
+    ys = np.stack([signals.hdr(100000, 10 + i) for i in range(5)])
+    big = torch.zeros(5, 100100, device="cuda")
+    big[:, :100000] = torch.from_numpy(ys).float().cuda()
+    mean = np.linspace(-5, 5, 64).astype(np.float32)
+    std = np.linspace(0.5, 2.0, 64).astype(np.float32)
+    out = P.waveform_to_log_mel(big[:, :100000], mean=mean, std=std).cpu().numpy()
+    ref = (R.waveform_to_log_mel(ys) - mean) / std          # SpectogramDataset.transform, logMel mode
+    assert out.shape == (5, 7, 64)
+    assert np.abs(out * std - ref * std).max() < TOL_DB
+
+
+def test_stft_and_complex_to_logmel_dropins():
+    y = signals.hdr(100000, 2)
+    s = P.multichannel_stft(y[:, None])
+    sr = R.multichannel_stft(y[:, None])
+    assert s.shape == sr.shape == (1, 7, 16385) and s.dtype == np.complex64
+    assert np.abs(s - sr).max() / np.abs(sr).max() < 1e-5
+    lm3 = P.multichannel_complex_to_log_mel(sr)
+    lm2 = P.multichannel_complex_to_log_mel(sr[0])          # 2-D input, Classical_methods/train_svm_detector.py:68
+    ref = R.multichannel_complex_to_log_mel(sr)
+    assert lm3.shape == (1, 7, 64) and lm2.shape == (7, 64) and lm3.dtype == np.float32
+    assert np.abs(lm3 - ref).max() < TOL_DB and np.abs(lm2 - ref[0]).max() < TOL_DB
+    two = np.stack([y, signals.white(100000, 4)], axis=1)    # two channels
+    s2 = P.multichannel_stft(two)
+    assert s2.shape == (2, 7, 16385)
+    assert np.abs(s2[0] - sr[0]).max() / np.abs(sr).max() < 1e-5
+
+
+def test_full_size_properties():
+    """BASELINE-sized batch (16 x 60 s clips): size-independent properties instead of the (slow) oracle."""
+    g = torch.Generator(device="cuda").manual_seed(0)
+    w = (torch.randn(16, 2880000, device="cuda", generator=g) * 0.1).clamp_(-1, 1)
+    a = P.waveform_to_log_mel(w)
+    assert a.shape == (16, 182, 64) and bool(torch.isfinite(a).all())
+    # power scaling: log-mel(2x) = log-mel(x) + 20 log10(2)
+    b = P.waveform_to_log_mel(w * 2.0)
+    assert float((b - a - 20 * np.log10(2.0)).abs().max()) < 2e-3
+    # clip independence / determinism: a clip alone equals the clip inside the batch, bit for bit
+    c = P.waveform_to_log_mel(w[5:6])
+    assert torch.equal(c[0], a[5])
+    # the oracle on two of the clips
+    for i in (0, 15):
+        ref = R.waveform_to_log_mel(w[i].cpu().numpy().astype(np.float64))
+        assert np.abs(a[i].cpu().numpy() - ref).max() < TOL_DB
+
+
+def test_error_behaviour():
+    with pytest.raises(_ext.SedbError, match="reflect padding"):
+        P.waveform_to_log_mel(torch.zeros(1, 16384, device="cuda"))
+    assert P.waveform_to_log_mel(torch.zeros(0, 40000, device="cuda")).shape == (0, 3, 64)
+    # all-zero audio sits on the amin floor
+    assert float(P.waveform_to_log_mel(torch.zeros(1, 40000, device="cuda")).max()) == -100.0
+
+
+def test_host_buffer_entry_point():
+    lib = _ext.load()
+    ys = np.stack([signals.hdr(60000, 20 + i) for i in range(3)]).astype(np.float32)
+    wave = torch.from_numpy(ys).pin_memory()
+    out = torch.empty(3, 4, 64).pin_memory()
+    _ext.check(lib.sedb_logmel_host_f32(_ext.context(), ctypes.c_void_p(wave.data_ptr()), 3, 60000, 60000, None,
+                                        ctypes.c_void_p(out.data_ptr())))
+    assert np.abs(out.numpy() - R.waveform_to_log_mel(ys.astype(np.float64))).max() < TOL_DB
