@@ -10,7 +10,7 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libsedb.so")
+_LIB_PATH = os.environ.get("SEDB_LIB_PATH") or os.path.join(_HERE, "libsedb.so")
 _lock = threading.Lock()
 _lib = None
 

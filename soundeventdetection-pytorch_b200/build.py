@@ -1,6 +1,6 @@
 """Builds libsedb.so (hand-written sm_100a kernels + C ABI) in-tree with nvcc.
 
-    python soundeventdetection-pytorch_b200/build.py [--fp16] [--force]
+    python soundeventdetection-pytorch_b200/build.py [--bf16] [--force] [-v]
 
 nvcc cross-compiles without a GPU.  The .so is git-ignored but travels to the GPU box with the repo snapshot.
 """
@@ -36,7 +36,7 @@ def needs_build() -> bool:
 
 def build(force: bool = False, fp16: bool | None = None, verbose: bool = False) -> str:
     if fp16 is None:
-        fp16 = os.environ.get("SEDB_SPLIT_FP16", "0") == "1"
+        fp16 = os.environ.get("SEDB_SPLIT_FP16", "1") == "1"
     if not force and not needs_build():
         return LIB
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -51,4 +51,4 @@ def build(force: bool = False, fp16: bool | None = None, verbose: bool = False) 
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, fp16=("--fp16" in sys.argv) or None, verbose="-v" in sys.argv))
+    print(build(force="--force" in sys.argv, fp16=False if "--bf16" in sys.argv else None, verbose="-v" in sys.argv))

@@ -42,21 +42,20 @@ inline void split_hi_lo(double v, bool fp16, uint16_t& hi, uint16_t& lo) {
     lo = to_split_bits(x - from_split_bits(hi, fp16), fp16);
 }
 
-// Stage-1 constants: 16 K-chunks x {cH, cL, sH, sL} x [128 rows k1][16 k = n1 - 16 c], K-major canonical
-// (byte = (k/8)*2048 + m*16 + (k%8)*2).  Row 0 of the sine block carries (-1)^n1, i.e. k1 = 128.
+// Stage-1 constants (even/odd folded real DFT over n1, K = 128): 8 K-chunks x {cH, cL, sH, sL} x
+// [128 rows k1][16 k = m - 16 c], K-major canonical (byte = (k/8)*2048 + row*16 + (k%8)*2);
+// c = cos(2 pi k1 m/256) multiplies U[m] = X[m] + X[256-m], s = -sin(2 pi k1 m/256) multiplies V[m] = X[m] - X[256-m].
 inline std::vector<uint8_t> make_stage1_constants(bool fp16) {
-    std::vector<uint8_t> buf(16 * 4 * 4096);
-    for (int c = 0; c < 16; ++c)
-        for (int m = 0; m < 128; ++m)
+    std::vector<uint8_t> buf(8 * 4 * 4096);
+    for (int c = 0; c < 8; ++c)
+        for (int row = 0; row < 128; ++row)
             for (int kk = 0; kk < 16; ++kk) {
-                const int n1 = 16 * c + kk;
-                const double ang = 2.0 * kPi * static_cast<double>((m * n1) % 256) / 256.0;
-                double cv = std::cos(ang), sv = -std::sin(ang);
-                if (m == 0) sv = (n1 & 1) ? -1.0 : 1.0;
+                const int m = 16 * c + kk;
+                const double ang = 2.0 * kPi * static_cast<double>((row * m) % 256) / 256.0;
                 uint16_t ch, cl, sh, sl;
-                split_hi_lo(cv, fp16, ch, cl);
-                split_hi_lo(sv, fp16, sh, sl);
-                const size_t off = static_cast<size_t>(c) * 16384 + (kk / 8) * 2048 + m * 16 + (kk % 8) * 2;
+                split_hi_lo(std::cos(ang), fp16, ch, cl);
+                split_hi_lo(-std::sin(ang), fp16, sh, sl);
+                const size_t off = static_cast<size_t>(c) * 16384 + (kk / 8) * 2048 + row * 16 + (kk % 8) * 2;
                 std::memcpy(&buf[off + 0 * 4096], &ch, 2);
                 std::memcpy(&buf[off + 1 * 4096], &cl, 2);
                 std::memcpy(&buf[off + 2 * 4096], &sh, 2);
@@ -65,23 +64,37 @@ inline std::vector<uint8_t> make_stage1_constants(bool fp16) {
     return buf;
 }
 
-// Stage-2 constants: {cH, cL, sH, sL} x [128 n = k2][128 k = n2], K-major canonical; c = cos, s = +sin of
-// 2 pi n2 k2 / 128 (exp(-i a) = c - i s).
+// Stage-2 constants (64-point complex DFT shared by the even and odd radix-2 halves): {breH, breL, bimH, bimL} x
+// [128 rows = output column][64 k = n], K-major canonical.  Output columns 0..63 are real parts, 64..127 imaginary:
+//   bre (multiplies the real part of the A operand) = [cos | -sin],  bim (imaginary part) = [sin | cos].
 inline std::vector<uint8_t> make_stage2_constants(bool fp16) {
-    std::vector<uint8_t> buf(4 * 32768);
-    for (int n = 0; n < 128; ++n)
-        for (int k = 0; k < 128; ++k) {
-            const double ang = 2.0 * kPi * static_cast<double>((n * k) % 128) / 128.0;
-            uint16_t ch, cl, sh, sl;
-            split_hi_lo(std::cos(ang), fp16, ch, cl);
-            split_hi_lo(std::sin(ang), fp16, sh, sl);
-            const size_t off = static_cast<size_t>(k / 8) * 2048 + n * 16 + (k % 8) * 2;
-            std::memcpy(&buf[off + 0 * 32768], &ch, 2);
-            std::memcpy(&buf[off + 1 * 32768], &cl, 2);
-            std::memcpy(&buf[off + 2 * 32768], &sh, 2);
-            std::memcpy(&buf[off + 3 * 32768], &sl, 2);
+    std::vector<uint8_t> buf(4 * 16384);
+    for (int col = 0; col < 128; ++col)
+        for (int k = 0; k < 64; ++k) {
+            const int j = col & 63;
+            const double ang = 2.0 * kPi * static_cast<double>((k * j) % 64) / 64.0;
+            const double cv = std::cos(ang), sv = std::sin(ang);
+            const double bre = (col < 64) ? cv : -sv;
+            const double bim = (col < 64) ? sv : cv;
+            uint16_t rh, rl, ih, il;
+            split_hi_lo(bre, fp16, rh, rl);
+            split_hi_lo(bim, fp16, ih, il);
+            const size_t off = static_cast<size_t>(k / 8) * 2048 + col * 16 + (k % 8) * 2;
+            std::memcpy(&buf[off + 0 * 16384], &rh, 2);
+            std::memcpy(&buf[off + 1 * 16384], &rl, 2);
+            std::memcpy(&buf[off + 2 * 16384], &ih, 2);
+            std::memcpy(&buf[off + 3 * 16384], &il, 2);
         }
     return buf;
+}
+
+// np.hanning(win) centre-padded with zeros to n_fft (librosa util.pad_center), float32.
+inline std::vector<float> make_hann_padded(int win, int n_fft) {
+    std::vector<float> w(n_fft, 0.f);
+    const int lpad = (n_fft - win) / 2;
+    for (int i = 0; i < win; ++i)
+        w[lpad + i] = static_cast<float>(0.5 - 0.5 * std::cos(2.0 * kPi * static_cast<double>(i) / (win - 1)));
+    return w;
 }
 
 // ---- librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax, htk=False, norm='slaney') --------------------
@@ -136,9 +149,15 @@ inline void make_mel_bands(const std::vector<float>& dense, int n_bins, int n_me
                 last = k;
             }
         if (first < 0) { first = 0; last = -1; }
-        tab[m] = {first, last - first + 1, static_cast<int>(weights.size()), 0};
-        for (int k = first; k <= last; ++k) weights.push_back(dense[static_cast<size_t>(k) * n_mels + m]);
-        while (weights.size() % 4) weights.push_back(0.f);
+        first &= ~3;                                            // bands start on a multiple of 4 bins (float4 loads)
+        int cnt = last - first + 1;
+        if (cnt < 0) cnt = 0;
+        const int cnt_pad = (cnt + 3) & ~3;
+        tab[m] = {first, cnt_pad, static_cast<int>(weights.size()), 0};
+        for (int i = 0; i < cnt_pad; ++i) {
+            const int k = first + i;
+            weights.push_back(k < n_bins ? dense[static_cast<size_t>(k) * n_mels + m] : 0.f);
+        }
     }
 }
 

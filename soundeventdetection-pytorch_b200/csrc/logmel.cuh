@@ -5,14 +5,20 @@
 //     multichannel_complex_to_log_mel(multichannel_stft(x))      (dataset/spectogram/preprocess.py:21-45)
 // without ever writing the (T x 16385) complex STFT to HBM.
 //
-// Algorithm (see DESIGN.md section "K1/K2"): N = 32768 = 256 (n1) x 128 (n2), n = 128 n1 + n2, k = k1 + 256 k2.
-//   stage 1  GEMM  Dc/Ds[k1,n2] = sum_n1 {cos,-sin}(2 pi k1 n1/256) g[128 n1 + n2]        (constants = A, frame = B)
-//   twiddle  CUDA  Z[k1,n2] = (Dc + i Ds) exp(-2 pi i k1 n2/32768)                         (TMEM -> regs -> smem)
-//   stage 2  GEMM  X[k1 + 256 k2] = sum_n2 Z[k1,n2] exp(-2 pi i n2 k2/128)                 (Z = A, constants = B)
-//   row 128  CUDA  X[128 + 256 k2] from Y[n2,128] (kept in row 0 of the sine block)
+// Algorithm (DESIGN.md "K1/K2"; numpy model in tests/dft_model.py::factored_power_spectrum_v2):
+//   N = 32768 = 256 (n1) x 128 (n2), frame g[128 n1 + n2] = X[n1,n2], bin k = k1 + 256 k2, k1 in [0,128].
+//   fold     CUDA  U[m] = X[m] + X[256-m], V[m] = X[m] - X[256-m]  (m = 1..127; U[0] = X[0], V[0] = 0)
+//   stage 1  GEMM  Dc[k1,n2] = sum_m cos(2 pi k1 m/256) U[m,n2],  Ds[k1,n2] = sum_m -sin(2 pi k1 m/256) V[m,n2]
+//                  (constants = A operand streamed by bulk copies, frame = B operand; K = 128)
+//   twiddle  CUDA  Z = (Dc + (-1)^k1 X[128] + i Ds) exp(-2 pi i k1 n2/32768)
+//   radix-2  CUDA  E[n] = Z[n] + Z[n+64],  O[n] = (Z[n] - Z[n+64]) exp(-2 pi i n/128)      n in [0,64)
+//   stage 2  GEMM  X[k1 + 256 (2j)]   = sum_n E[k1,n] exp(-2 pi i n j/64)
+//                  X[k1 + 256 (2j+1)] = sum_n O[k1,n] exp(-2 pi i n j/64)   (E/O = A operand, constants = B, resident)
+//   row 128  CUDA  X[128 + 256 k2] from Y[n2,128] = sum_m (-1)^m U[m,n2] + X[128,n2]
 //   power, Hermitian bin map, banded mel dot products, 10 log10(max(1e-10, .)).
-// All GEMM operands are split x = hi + lo (two 16-bit floats) and multiplied as hi*hi + lo*hi + hi*lo with
-// fp32 accumulation in TMEM, which keeps the DFT at ~2^-17 (bf16) / 2^-22 (fp16) relative accuracy.
+// GEMM operands are split x = hi + lo (two 16-bit floats) and multiplied as hi*hi + lo*hi + hi*lo with fp32
+// accumulation in TMEM: ~2^-17 relative with bf16 halves, ~2^-22 with fp16 halves (SEDB_SPLIT_FP16=1, which adds a
+// per-frame power-of-two block scale so that the fp16 range is never exceeded).
 #pragma once
 #include "umma.cuh"
 
@@ -28,34 +34,38 @@ constexpr int kLpad = (kNfft - kWin) / 2;   // 544 zeros each side of the window
 constexpr int kPadRefl = kNfft / 2;         // 16384 reflect-padded samples each side (center=True)
 
 // ---- shared memory map of the fused kernel -------------------------------------------------------------
-constexpr int kB2ArrBytes = 128 * 128 * 2;                 // one resident stage-2 constant array (32 KB)
-constexpr int kB2Bytes = 4 * kB2ArrBytes;                  // cH | cL | sH | sL
+constexpr int kB2ArrBytes = 128 * 64 * 2;                  // one resident stage-2 constant array [N=128][K=64] (16 KB)
+constexpr int kB2Bytes = 4 * kB2ArrBytes;                  // breH | breL | bimH | bimL
 constexpr int kA1ArrBytes = 128 * 16 * 2;                  // one stage-1 constant array per K-chunk (4 KB)
 constexpr int kA1ChunkBytes = 4 * kA1ArrBytes;             // cH | cL | sH | sL  (16 KB)
 constexpr int kB1Sbo = 144;                                // padded stride between 8-sample groups (bank spread)
 constexpr int kB1Lbo = 16 * kB1Sbo;                        // 2304: stride between groups of 8 rows (K)
 constexpr int kB1ArrBytes = 2 * kB1Lbo;                    // 4608
-constexpr int kSlotBytes = 26624;                          // >= 16384 + 2*4608 (stage 1) and >= 6*4096 (stage 2)
-constexpr int kNumSlots = 3;
-constexpr int kRingBytes = kSlotBytes * kNumSlots;         // 79872 >= 16385*4 (power spectrum aliases the ring)
+constexpr int kSlotBytes = kA1ChunkBytes + 4 * kB1ArrBytes; // 34816: stage 1 (A1 + UH UL VH VL); stage 2 uses 8 x 4 KB
+constexpr int kNumSlots = 4;
+constexpr int kRingBytes = kSlotBytes * kNumSlots;         // 139264 (the power spectrum aliases the ring)
 constexpr int kA2ArrBytes = 128 * 16 * 2;                  // 4 KB
+static_assert(8 * kA2ArrBytes <= kSlotBytes, "stage-2 operands must fit a slot");
 
 constexpr int kOffB2 = 0;
-constexpr int kOffRing = kOffB2 + kB2Bytes;                // 131072
-constexpr int kOffV = kOffRing + kRingBytes;               // Y[n2,128]   128 floats
+constexpr int kOffRing = kOffB2 + kB2Bytes;                // 65536
+constexpr int kOffAlt = kOffRing + kRingBytes;             // per-row alternating partial sums  [16][128] floats
+constexpr int kOffX128 = kOffAlt + 16 * 128 * 4;           // X[128, n2]      128 floats
+constexpr int kOffV = kOffX128 + 512;                      // Y[n2,128]       128 floats
 constexpr int kOffCs = kOffV + 512;                        // exp(-2 pi i j/256) 256 float2
 constexpr int kOffMelTab = kOffCs + 2048;                  // 64 x int4 {lo, cnt, woff, 0}
-constexpr int kOffBars = kOffMelTab + 1024;                // mbarriers
+constexpr int kOffRed = kOffMelTab + 1024;                 // absmax reduction scratch (16 floats) + scale
+constexpr int kOffBars = kOffRed + 128;                    // mbarriers
 constexpr int kOffTmem = kOffBars + 256;                   // tmem base address
 constexpr int kSmemBytes = kOffTmem + 16;
-static_assert(kRingBytes >= kBins * 4, "power spectrum must fit in the ring");
+static_assert(kRingBytes >= (kBins + 3) * 4, "power spectrum must fit in the ring");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
-constexpr int kWorkerWarps = 8;
+constexpr int kWorkerWarps = 16;
 constexpr int kWorkerThreads = kWorkerWarps * 32;
-constexpr int kMmaWarp = 8;
-constexpr int kCopyWarp = 9;
-constexpr int kThreads = 320;
+constexpr int kMmaWarp = 16;
+constexpr int kCopyWarp = 17;
+constexpr int kThreads = 576;
 
 struct LogmelParams {
     const float* wave;        // [B, wave_stride] fp32
@@ -63,25 +73,18 @@ struct LogmelParams {
     int n_samples;            // valid samples per clip
     int n_clips;
     int n_frames;             // T = 1 + n_samples / hop
-    const uint8_t* a1;        // stage-1 constants, 16 chunks x 16 KB, canonical K-major, split hi/lo
-    const uint8_t* b2;        // stage-2 constants, 4 x 32 KB
+    const uint8_t* a1;        // stage-1 constants, 8 chunks x 16 KB, canonical K-major, split hi/lo
+    const uint8_t* b2;        // stage-2 constants, 4 x 16 KB
+    const float* hann;        // np.hanning(31680) centre-padded to 32768
     const float* mel_w;       // compact mel weights (band of filter m starts at mel_tab[m].z)
-    const int4* mel_tab;      // 64 x {first bin, count, weight offset, 0}
+    const int4* mel_tab;      // 64 x {first bin (multiple of 4), padded count, weight offset, 0}
     const float* norm;        // nullable: mean[64] then std[64]  (SpectogramDataset.transform, logMel mode)
     float* out;               // MODE 0: [B, T, 64] fp32 log-mel
     float2* spec;             // MODE 1: [B, T, 16385] complex64 STFT
 };
 
-// named barrier among the 256 worker threads only
-__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-
-__device__ __forceinline__ float hann_padded(int n) {
-    // np.hanning(31680) centre-padded to 32768: 0.5 - 0.5 cos(2 pi (n-544)/31679) on [544, 32224), else 0.
-    // cos(2 pi f) = -cos(2 pi (f - 0.5)), argument kept in [-pi, pi] for the fast intrinsic.
-    float f = static_cast<float>(n - kLpad) * (1.0f / static_cast<float>(kWin - 1));
-    float c = __cosf((f - 0.5f) * 6.283185307179586f);
-    return 0.5f + 0.5f * c;
-}
+// named barrier among the worker threads only
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 __device__ __forceinline__ int reflect_index(int j, int n) {
     // np.pad(mode='reflect') for a pad shorter than the signal: -1 -> 1, n -> n-2
@@ -90,26 +93,59 @@ __device__ __forceinline__ int reflect_index(int j, int n) {
     return j;
 }
 
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+
+// 8 consecutive 32-bit TMEM columns of this warp's 32 lanes
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// split 8 floats into packed hi / lo halves (16 B each)
+__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) split_pack2(x[2 * i], x[2 * i + 1], h[i], l[i]);
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
 // Banded mel dot products over a power spectrum in shared memory, then dB (+ optional normalisation).
-// Called by the 8 worker warps; warp w owns filters w, w+8, ...
+// Called by `nwarps` warps; warp w owns filters w, w+nwarps, ...  Bands start on multiples of 4 bins.
 __device__ __forceinline__ void mel_db_from_smem(const float* __restrict__ p_s, const int4* __restrict__ mel_tab_s,
                                                  const float* __restrict__ mel_w, const float* __restrict__ norm,
-                                                 float inv_scale2, float* __restrict__ out_row, int warp, int lane) {
+                                                 float inv_scale2, float* __restrict__ out_row, int warp, int lane,
+                                                 int nwarps) {
     float mine = 0.f;
+    const int per_warp = kMel / nwarps;
 #pragma unroll 1
-    for (int i = 0; i < kMel / kWorkerWarps; ++i) {
-        const int m = warp + i * kWorkerWarps;
+    for (int i = 0; i < per_warp; ++i) {
+        const int m = warp + i * nwarps;
         const int4 tab = mel_tab_s[m];
-        const float* w = mel_w + tab.z;
-        const float* p = p_s + tab.x;
+        const float4* w = reinterpret_cast<const float4*>(mel_w + tab.z);
+        const float4* p = reinterpret_cast<const float4*>(p_s + tab.x);
         float acc = 0.f;
-        for (int j = lane; j < tab.y; j += 32) acc = fmaf(p[j], __ldg(w + j), acc);
+        for (int j = lane; j < (tab.y >> 2); j += 32) {
+            const float4 pv = p[j];
+            const float4 wv = __ldg(w + j);
+            acc = fmaf(pv.x, wv.x, acc);
+            acc = fmaf(pv.y, wv.y, acc);
+            acc = fmaf(pv.z, wv.z, acc);
+            acc = fmaf(pv.w, wv.w, acc);
+        }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == i) mine = acc;
     }
-    if (lane < kMel / kWorkerWarps) {
-        const int m = warp + lane * kWorkerWarps;
+    if (lane < per_warp) {
+        const int m = warp + lane * nwarps;
         float db = 10.0f * log10f(fmaxf(1e-10f, mine * inv_scale2));     // librosa.power_to_db(ref=1, amin=1e-10)
         if (norm != nullptr) db = (db - norm[m]) / norm[kMel + m];       // spectograms_dataset.py:105
         out_row[m] = db;
@@ -122,16 +158,18 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
     uint8_t* b2_s = smem + kOffB2;
     uint8_t* ring = smem + kOffRing;
     float* p_s = reinterpret_cast<float*>(ring);
+    float* alt_s = reinterpret_cast<float*>(smem + kOffAlt);
+    float* x128_s = reinterpret_cast<float*>(smem + kOffX128);
     float* v_s = reinterpret_cast<float*>(smem + kOffV);
     float2* cs_s = reinterpret_cast<float2*>(smem + kOffCs);
     int4* mel_tab_s = reinterpret_cast<int4*>(smem + kOffMelTab);
+    float* red_s = reinterpret_cast<float*>(smem + kOffRed);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
-    uint64_t* full1 = bars + 0;      // [3] stage-1 slot filled (8 worker warps + 1 bulk copy)
-    uint64_t* empty1 = bars + 3;     // [3] stage-1 slot consumed (tcgen05.commit)
-    uint64_t* full2 = bars + 6;      // [3] stage-2 slot filled (4 worker warps)
-    uint64_t* empty2 = bars + 9;     // [3] stage-2 slot consumed
+    uint64_t* full1 = bars + 0;      // [4] stage-1 slot filled (16 worker warps + 1 bulk copy)
+    uint64_t* empty1 = bars + 4;     // [4] stage-1 slot consumed (tcgen05.commit)
+    uint64_t* full2 = bars + 8;      // [4] stage-2 slot filled (4 worker warps)
     uint64_t* d1_full = bars + 12;   // stage-1 accumulators complete
     uint64_t* d2_full = bars + 13;   // stage-2 accumulators complete
     uint64_t* ring_free = bars + 14; // workers finished the frame (power spectrum no longer aliases the ring)
@@ -146,7 +184,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
             mbar_init(&full1[s], kWorkerWarps + 1);
             mbar_init(&empty1[s], 1);
             mbar_init(&full2[s], 4);
-            mbar_init(&empty2[s], 1);
         }
         mbar_init(d1_full, 1);
         mbar_init(d2_full, 1);
@@ -179,13 +216,23 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 bulk_g2s(b2_s + a * kB2ArrBytes, prm.b2 + a * kB2ArrBytes, kB2ArrBytes, b2_full);
             for (int it = 0; it < n_iter; ++it) {
                 if (it > 0) mbar_wait(ring_free, (it - 1) & 1);
-                for (int c = 0; c < 16; ++c) {
-                    const int g = it * 16 + c;
+                for (int c = 0; c < 8; ++c) {
+                    const int g = it * 8 + c;
                     const int s = g % kNumSlots;
                     const int u = g / kNumSlots;
                     mbar_wait(&empty1[s], (u & 1) ^ 1);
                     mbar_arrive_expect_tx(&full1[s], kA1ChunkBytes);
                     bulk_g2s(ring + s * kSlotBytes, prm.a1 + c * kA1ChunkBytes, kA1ChunkBytes, &full1[s]);
+                }
+                // pull the next frame's samples towards L2 while this one is being processed
+                if (it + 1 < n_iter) {
+                    const long long f = blockIdx.x + static_cast<long long>(it + 1) * gridDim.x;
+                    const int clip = static_cast<int>(f / prm.n_frames);
+                    const int t = static_cast<int>(f - static_cast<long long>(clip) * prm.n_frames);
+                    const long long j0 = static_cast<long long>(t) * kHop + kLpad - kPadRefl;
+                    const float* src = prm.wave + static_cast<long long>(clip) * prm.wave_stride + j0;
+                    if (j0 >= 0 && j0 + kWin <= prm.n_samples && (reinterpret_cast<uintptr_t>(src) & 15) == 0)
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(kWin * 4) : "memory");
                 }
             }
         }
@@ -199,9 +246,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
             const uint32_t b2_a = smem_u32(b2_s);
             mbar_wait(b2_full, 0);
             for (int it = 0; it < n_iter; ++it) {
-                // ---------------- stage 1: 16 K-chunks of 16 rows (n1)
-                for (int c = 0; c < 16; ++c) {
-                    const int g = it * 16 + c;
+                // ---------------- stage 1: 8 K-chunks of 16 folded rows (m)
+                for (int c = 0; c < 8; ++c) {
+                    const int g = it * 8 + c;
                     const int s = g % kNumSlots;
                     const int u = g / kNumSlots;
                     mbar_wait(&full1[s], u & 1);
@@ -211,83 +258,83 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                     const uint64_t cL = make_smem_desc(slot + 1 * kA1ArrBytes, 2048, 128);
                     const uint64_t sH = make_smem_desc(slot + 2 * kA1ArrBytes, 2048, 128);
                     const uint64_t sL = make_smem_desc(slot + 3 * kA1ArrBytes, 2048, 128);
-                    const uint64_t xH = make_smem_desc(slot + kA1ChunkBytes, kB1Lbo, kB1Sbo);
-                    const uint64_t xL = make_smem_desc(slot + kA1ChunkBytes + kB1ArrBytes, kB1Lbo, kB1Sbo);
+                    const uint32_t bb = slot + kA1ChunkBytes;
+                    const uint64_t uH = make_smem_desc(bb + 0 * kB1ArrBytes, kB1Lbo, kB1Sbo);
+                    const uint64_t uL = make_smem_desc(bb + 1 * kB1ArrBytes, kB1Lbo, kB1Sbo);
+                    const uint64_t vH = make_smem_desc(bb + 2 * kB1ArrBytes, kB1Lbo, kB1Sbo);
+                    const uint64_t vL = make_smem_desc(bb + 3 * kB1ArrBytes, kB1Lbo, kB1Sbo);
                     const uint32_t acc = (c > 0) ? 1u : 0u;
-                    umma_f16(tmem + 0, cH, xH, idesc1, acc);
-                    umma_f16(tmem + 0, cL, xH, idesc1, 1u);
-                    umma_f16(tmem + 0, cH, xL, idesc1, 1u);
-                    umma_f16(tmem + 128, sH, xH, idesc1, acc);
-                    umma_f16(tmem + 128, sL, xH, idesc1, 1u);
-                    umma_f16(tmem + 128, sH, xL, idesc1, 1u);
+                    umma_f16(tmem + 0, cH, uH, idesc1, acc);
+                    umma_f16(tmem + 0, cL, uH, idesc1, 1u);
+                    umma_f16(tmem + 0, cH, uL, idesc1, 1u);
+                    umma_f16(tmem + 128, sH, vH, idesc1, acc);
+                    umma_f16(tmem + 128, sL, vH, idesc1, 1u);
+                    umma_f16(tmem + 128, sH, vL, idesc1, 1u);
                     umma_commit(&empty1[s]);
                 }
                 umma_commit(d1_full);
-                // ---------------- stage 2: 8 K-chunks of 16 columns (n2), consumption order 0,4,1,5,...
-                for (int j = 0; j < 8; ++j) {
-                    const int g = it * 8 + j;
-                    const int s = g % kNumSlots;
-                    const int u = g / kNumSlots;
-                    const int chunk = (j & 1) * 4 + (j >> 1);
-                    mbar_wait(&full2[s], u & 1);
+                // ---------------- stage 2: 4 K-chunks of 16 columns (n), even and odd outputs
+                for (int j = 0; j < 4; ++j) {
+                    mbar_wait(&full2[j], it & 1);
                     tc_fence_after();
-                    const uint32_t slot = ring_a + s * kSlotBytes;
-                    const uint64_t zrH = make_smem_desc(slot + 0 * kA2ArrBytes, 2048, 128);
-                    const uint64_t zrL = make_smem_desc(slot + 1 * kA2ArrBytes, 2048, 128);
-                    const uint64_t ziH = make_smem_desc(slot + 2 * kA2ArrBytes, 2048, 128);
-                    const uint64_t ziL = make_smem_desc(slot + 3 * kA2ArrBytes, 2048, 128);
-                    const uint64_t nrH = make_smem_desc(slot + 4 * kA2ArrBytes, 2048, 128);
-                    const uint64_t nrL = make_smem_desc(slot + 5 * kA2ArrBytes, 2048, 128);
-                    const uint32_t koff = static_cast<uint32_t>(chunk) * 2 * 2048;   // 16 n2 = 2 K-groups
-                    const uint64_t cH = make_smem_desc(b2_a + 0 * kB2ArrBytes + koff, 2048, 128);
-                    const uint64_t cL = make_smem_desc(b2_a + 1 * kB2ArrBytes + koff, 2048, 128);
-                    const uint64_t sH = make_smem_desc(b2_a + 2 * kB2ArrBytes + koff, 2048, 128);
-                    const uint64_t sL = make_smem_desc(b2_a + 3 * kB2ArrBytes + koff, 2048, 128);
+                    const uint32_t slot = ring_a + j * kSlotBytes;
+                    uint64_t a[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) a[i] = make_smem_desc(slot + i * kA2ArrBytes, 2048, 128);
+                    const uint32_t koff = static_cast<uint32_t>(j) * 2 * 2048;       // 16 n = 2 K-groups
+                    const uint64_t reH = make_smem_desc(b2_a + 0 * kB2ArrBytes + koff, 2048, 128);
+                    const uint64_t reL = make_smem_desc(b2_a + 1 * kB2ArrBytes + koff, 2048, 128);
+                    const uint64_t imH = make_smem_desc(b2_a + 2 * kB2ArrBytes + koff, 2048, 128);
+                    const uint64_t imL = make_smem_desc(b2_a + 3 * kB2ArrBytes + koff, 2048, 128);
                     const uint32_t acc = (j > 0) ? 1u : 0u;
-                    // re = Zr c + Zi s
-                    umma_f16(tmem + 256, zrH, cH, idesc2, acc);
-                    umma_f16(tmem + 256, zrL, cH, idesc2, 1u);
-                    umma_f16(tmem + 256, zrH, cL, idesc2, 1u);
-                    umma_f16(tmem + 256, ziH, sH, idesc2, 1u);
-                    umma_f16(tmem + 256, ziL, sH, idesc2, 1u);
-                    umma_f16(tmem + 256, ziH, sL, idesc2, 1u);
-                    // im = Zi c - Zr s
-                    umma_f16(tmem + 384, ziH, cH, idesc2, acc);
-                    umma_f16(tmem + 384, ziL, cH, idesc2, 1u);
-                    umma_f16(tmem + 384, ziH, cL, idesc2, 1u);
-                    umma_f16(tmem + 384, nrH, sH, idesc2, 1u);
-                    umma_f16(tmem + 384, nrL, sH, idesc2, 1u);
-                    umma_f16(tmem + 384, nrH, sL, idesc2, 1u);
-                    umma_commit(&empty2[s]);
+#pragma unroll
+                    for (int par = 0; par < 2; ++par) {
+                        // a[4 par + {0,1,2,3}] = real hi, real lo, imag hi, imag lo of E (par 0) / O (par 1)
+                        const uint32_t d = tmem + 256 + 128 * par;
+                        umma_f16(d, a[4 * par + 0], reH, idesc2, acc);
+                        umma_f16(d, a[4 * par + 1], reH, idesc2, 1u);
+                        umma_f16(d, a[4 * par + 0], reL, idesc2, 1u);
+                        umma_f16(d, a[4 * par + 2], imH, idesc2, 1u);
+                        umma_f16(d, a[4 * par + 3], imH, idesc2, 1u);
+                        umma_f16(d, a[4 * par + 2], imL, idesc2, 1u);
+                    }
                 }
                 umma_commit(d2_full);
             }
         }
     }
-    // ======================================================================== 8 worker warps
+    // ======================================================================== 16 worker warps
     else {
         const int q = warp & 3;                 // TMEM lane quarter
-        const int h = warp >> 2;                // column half
+        const int cg = warp >> 2;               // column group: n in [16 cg, 16 cg + 16) (and + 64)
         const int k1 = q * 32 + lane;           // this thread's stage-1 output row / stage-2 A row
         const uint32_t tlane = tmem + (static_cast<uint32_t>(q * 32) << 16);
+        const float sgn_k1 = (k1 & 1) ? -1.f : 1.f;
 
-        // per-thread twiddle bases: w1^j (j=0..3), w1^(4i) (i=0..3), anchors w1^(16 cc + 64 h) (cc=0..3)
-        float2 wj[4], w4[4], anc[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
+        // per-thread twiddle constants: W^j (j=1..3), W^4, anchors W^(16 cg + 8 hb), W^64; W = exp(-2 pi i k1/32768)
+        float2 wj[4], w4, anc[2], w64;
+        {
             float s, c;
-            sincospif(static_cast<float>(k1 * j) * (1.0f / 16384.0f), &s, &c);
-            wj[j] = make_float2(c, -s);
-            sincospif(static_cast<float>(k1 * 4 * j) * (1.0f / 16384.0f), &s, &c);
-            w4[j] = make_float2(c, -s);
-            sincospif(static_cast<float>(k1 * (16 * j + 64 * h)) * (1.0f / 16384.0f), &s, &c);
-            anc[j] = make_float2(c, -s);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                sincospif(static_cast<float>(k1 * j) * (1.0f / 16384.0f), &s, &c);
+                wj[j] = make_float2(c, -s);
+            }
+            sincospif(static_cast<float>(k1 * 4) * (1.0f / 16384.0f), &s, &c);
+            w4 = make_float2(c, -s);
+#pragma unroll
+            for (int hb = 0; hb < 2; ++hb) {
+                sincospif(static_cast<float>(k1 * (16 * cg + 8 * hb)) * (1.0f / 16384.0f), &s, &c);
+                anc[hb] = make_float2(c, -s);
+            }
+            sincospif(static_cast<float>(k1 * 64) * (1.0f / 16384.0f), &s, &c);
+            w64 = make_float2(c, -s);
         }
 
-        // stage-1 producer mapping: thread -> (row r of the 16-row chunk, group g of 8 samples)
-        const int r = tid >> 4;                 // 0..15
-        const int grp = tid & 15;               // 0..15
-        const uint32_t b1_off = kA1ChunkBytes + grp * kB1Sbo + (r >> 3) * kB1Lbo + (r & 7) * 16;
+        // stage-1 producer mapping: warp -> row r of the 16-row chunk, lane -> 4 consecutive samples
+        const int r = warp;
+        const uint32_t b1_off = kA1ChunkBytes + (lane >> 1) * kB1Sbo + (r >> 3) * kB1Lbo + (r & 7) * 16 + (lane & 1) * 8;
+        const float alt_sign = (r & 1) ? -1.f : 1.f;
 
         for (int it = 0; it < n_iter; ++it) {
             const long long f = blockIdx.x + static_cast<long long>(it) * gridDim.x;
@@ -297,111 +344,156 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
             const int L = prm.n_samples;
             const bool vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
 
-            // ---------------------------------------------------------------- stage 1: window + split
-            float x[8];
-            auto load_chunk = [&](int c) {
-                const int n0 = 128 * (16 * c + r) + 8 * grp;          // position inside the padded frame
-                const int j0 = t * kHop + n0 - kPadRefl;              // position inside the clip
-                if (n0 < kLpad || n0 >= kLpad + kWin) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) x[e] = 0.f;
-                } else if (vec_ok && j0 >= 0 && j0 + 8 <= L) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(y + j0));
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(y + j0 + 4));
-                    x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w;
-                    x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) x[e] = __ldg(y + reflect_index(j0 + e, L));
-                }
+            // ---------------------------------------------------------------- load the frame into registers
+            // chunk c, this thread: rows m = 16 c + r and 256 - m (row 128 for m = 0), samples n2 = 4 lane .. +3
+            float4 xa[8], xb[8];
+            auto load4 = [&](int n0) -> float4 {
+                const int j0 = t * kHop + n0 - kPadRefl;
+                if (n0 < kLpad - 3 || n0 >= kLpad + kWin) return make_float4(0.f, 0.f, 0.f, 0.f);   // window is zero
+                if (vec_ok && j0 >= 0 && j0 + 4 <= L) return __ldg(reinterpret_cast<const float4*>(y + j0));
+                float4 v;
+                v.x = __ldg(y + reflect_index(j0 + 0, L));
+                v.y = __ldg(y + reflect_index(j0 + 1, L));
+                v.z = __ldg(y + reflect_index(j0 + 2, L));
+                v.w = __ldg(y + reflect_index(j0 + 3, L));
+                return v;
             };
-            load_chunk(0);
-#pragma unroll 1
-            for (int c = 0; c < 16; ++c) {
-                const int g = it * 16 + c;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int m = 16 * c + r;
+                const int mb = (m == 0) ? 128 : 256 - m;
+                xa[c] = load4(128 * m + 4 * lane);
+                xb[c] = load4(128 * mb + 4 * lane);
+            }
+            // ---------------------------------------------------------------- per-frame block scale (fp16 halves)
+            float scale = 1.0f, inv_scale = 1.0f;
+#if SEDB_SPLIT_FP16
+            {
+                float mx = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(xa[c].x), fabsf(xa[c].y)), fmaxf(fabsf(xa[c].z), fabsf(xa[c].w))));
+                    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(xb[c].x), fabsf(xb[c].y)), fmaxf(fabsf(xb[c].z), fabsf(xb[c].w))));
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                if (lane == 0) red_s[warp] = mx;
+                worker_sync();
+                mx = red_s[lane & 15];
+#pragma unroll
+                for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+                // scale = 2^(5 - floor(log2 max)): |x| scale < 64, so no intermediate can exceed 2^15 < 65504
+                int e = 0;
+                if (mx > 0.f && mx < 3.0e38f) e = 5 - (static_cast<int>((__float_as_uint(mx) >> 23) & 0xff) - 127);
+                e = max(-56, min(60, e));
+                scale = __uint_as_float(static_cast<uint32_t>(127 + e) << 23);
+                inv_scale = __uint_as_float(static_cast<uint32_t>(127 - e) << 23);
+            }
+#endif
+            // ---------------------------------------------------------------- stage 1: window, fold, split
+            float alt[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const int g = it * 8 + c;
                 const int s = g % kNumSlots;
                 const int u = g / kNumSlots;
-                const int n0 = 128 * (16 * c + r) + 8 * grp;
-                uint32_t hi[4], lo[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    float a = x[2 * e], b = x[2 * e + 1];
-                    if (n0 >= kLpad && n0 < kLpad + kWin) {
-                        a *= hann_padded(n0 + 2 * e);
-                        b *= hann_padded(n0 + 2 * e + 1);
-                    }
-                    split_pack2(a, b, hi[e], lo[e]);
+                const int m = 16 * c + r;
+                const int mb = (m == 0) ? 128 : 256 - m;
+                const float4 wa = __ldg(reinterpret_cast<const float4*>(prm.hann + 128 * m + 4 * lane));
+                const float4 wb = __ldg(reinterpret_cast<const float4*>(prm.hann + 128 * mb + 4 * lane));
+                const float a0 = xa[c].x * wa.x * scale, a1 = xa[c].y * wa.y * scale;
+                const float a2 = xa[c].z * wa.z * scale, a3 = xa[c].w * wa.w * scale;
+                const float b0 = xb[c].x * wb.x * scale, b1 = xb[c].y * wb.y * scale;
+                const float b2 = xb[c].z * wb.z * scale, b3 = xb[c].w * wb.w * scale;
+                float u4[4], v4[4];
+                if (m == 0) {                                   // warp-uniform: U[0] = X[0], V[0] = 0, keep X[128]
+                    u4[0] = a0; u4[1] = a1; u4[2] = a2; u4[3] = a3;
+                    v4[0] = v4[1] = v4[2] = v4[3] = 0.f;
+                    *reinterpret_cast<float4*>(x128_s + 4 * lane) = make_float4(b0, b1, b2, b3);
+                } else {
+                    u4[0] = a0 + b0; u4[1] = a1 + b1; u4[2] = a2 + b2; u4[3] = a3 + b3;
+                    v4[0] = a0 - b0; v4[1] = a1 - b1; v4[2] = a2 - b2; v4[3] = a3 - b3;
                 }
-                if (c + 1 < 16) load_chunk(c + 1);                    // prefetch next chunk's samples
+#pragma unroll
+                for (int e = 0; e < 4; ++e) alt[e] += u4[e];
+                uint32_t uh[2], ul[2], vh[2], vl[2];
+                split_pack2(u4[0], u4[1], uh[0], ul[0]);
+                split_pack2(u4[2], u4[3], uh[1], ul[1]);
+                split_pack2(v4[0], v4[1], vh[0], vl[0]);
+                split_pack2(v4[2], v4[3], vh[1], vl[1]);
                 mbar_wait(&empty1[s], (u & 1) ^ 1);
                 uint8_t* dst = ring + s * kSlotBytes + b1_off;
-                *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-                *reinterpret_cast<uint4*>(dst + kB1ArrBytes) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+                *reinterpret_cast<uint2*>(dst + 0 * kB1ArrBytes) = make_uint2(uh[0], uh[1]);
+                *reinterpret_cast<uint2*>(dst + 1 * kB1ArrBytes) = make_uint2(ul[0], ul[1]);
+                *reinterpret_cast<uint2*>(dst + 2 * kB1ArrBytes) = make_uint2(vh[0], vh[1]);
+                *reinterpret_cast<uint2*>(dst + 3 * kB1ArrBytes) = make_uint2(vl[0], vl[1]);
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full1[s]);
             }
+            // alternating row sums for k1 = 128: row r of every chunk has parity r
+            *reinterpret_cast<float4*>(alt_s + r * 128 + 4 * lane) =
+                make_float4(alt_sign * alt[0], alt_sign * alt[1], alt_sign * alt[2], alt_sign * alt[3]);
 
-            // ---------------------------------------------------------------- twiddle + stage-2 A operand
+            // ---------------------------------------------------------------- twiddle, radix-2, stage-2 A operand
             mbar_wait(d1_full, it & 1);
             tc_fence_after();
+            worker_sync();                                            // x128_s / alt_s visible to all workers
+            if (tid < 128) {
+                float acc = x128_s[tid];
+#pragma unroll
+                for (int rr = 0; rr < 16; ++rr) acc += alt_s[rr * 128 + tid];
+                v_s[tid] = acc;                                       // Y[n2,128] (scaled)
+            }
+            {
+                uint8_t* dst = ring + cg * kSlotBytes + k1 * 16;
 #pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
-                const int j = cc * 2 + h;                             // consumption order index
-                const int g = it * 8 + j;
-                const int s = g % kNumSlots;
-                const int u = g / kNumSlots;
-                const int n2_0 = 64 * h + 16 * cc;
-                float yr[16], yi[16];
-                tmem_ld16(tlane + n2_0, yr);
-                tmem_ld16(tlane + 128 + n2_0, yi);
-                tmem_ld_wait();
-                if (k1 == 0) {
+                for (int hb = 0; hb < 2; ++hb) {
+                    const int n0 = 16 * cg + 8 * hb;
+                    float c0[8], c1[8], s0[8], s1[8];
+                    tmem_ld8(tlane + n0, c0);
+                    tmem_ld8(tlane + 64 + n0, c1);
+                    tmem_ld8(tlane + 128 + n0, s0);
+                    tmem_ld8(tlane + 192 + n0, s1);
+                    tmem_ld_wait();
+                    float er[8], ei[8], orr[8], oi[8];
 #pragma unroll
-                    for (int i = 0; i < 16; ++i) { v_s[n2_0 + i] = yi[i]; yi[i] = 0.f; }
-                }
-                uint32_t zrh[8], zrl[8], zih[8], zil[8];
+                    for (int i4 = 0; i4 < 2; ++i4) {
+                        const float2 tb = (i4 == 0) ? anc[hb] : cmul(anc[hb], w4);
 #pragma unroll
-                for (int i4 = 0; i4 < 4; ++i4) {
-                    // base twiddle for columns n2_0 + 4*i4 .. +3
-                    const float2 tb = make_float2(anc[cc].x * w4[i4].x - anc[cc].y * w4[i4].y,
-                                                  anc[cc].x * w4[i4].y + anc[cc].y * w4[i4].x);
-                    float zr[4], zi[4];
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const float twr = tb.x * wj[jj].x - tb.y * wj[jj].y;
-                        const float twi = tb.x * wj[jj].y + tb.y * wj[jj].x;
-                        const int i = i4 * 4 + jj;
-                        zr[jj] = yr[i] * twr - yi[i] * twi;
-                        zi[jj] = yr[i] * twi + yi[i] * twr;
+                        for (int jj = 0; jj < 4; ++jj) {
+                            const int i = 4 * i4 + jj;
+                            const float2 tw0 = (jj == 0) ? tb : cmul(tb, wj[jj]);
+                            const float2 tw1 = cmul(tw0, w64);
+                            const float yr0 = fmaf(sgn_k1, x128_s[n0 + i], c0[i]);
+                            const float yr1 = fmaf(sgn_k1, x128_s[64 + n0 + i], c1[i]);
+                            const float2 z0 = cmul(make_float2(yr0, s0[i]), tw0);
+                            const float2 z1 = cmul(make_float2(yr1, s1[i]), tw1);
+                            er[i] = z0.x + z1.x;
+                            ei[i] = z0.y + z1.y;
+                            const float2 o = cmul(make_float2(z0.x - z1.x, z0.y - z1.y), cs_s[2 * (n0 + i)]);
+                            orr[i] = o.x;
+                            oi[i] = o.y;
+                        }
                     }
-                    split_pack2(zr[0], zr[1], zrh[i4 * 2], zrl[i4 * 2]);
-                    split_pack2(zr[2], zr[3], zrh[i4 * 2 + 1], zrl[i4 * 2 + 1]);
-                    split_pack2(zi[0], zi[1], zih[i4 * 2], zil[i4 * 2]);
-                    split_pack2(zi[2], zi[3], zih[i4 * 2 + 1], zil[i4 * 2 + 1]);
-                }
-                mbar_wait(&empty2[s], (u & 1) ^ 1);
-                uint8_t* dst = ring + s * kSlotBytes + k1 * 16;
-#pragma unroll
-                for (int kg = 0; kg < 2; ++kg) {
-                    const uint4 vrh = make_uint4(zrh[kg * 4], zrh[kg * 4 + 1], zrh[kg * 4 + 2], zrh[kg * 4 + 3]);
-                    const uint4 vrl = make_uint4(zrl[kg * 4], zrl[kg * 4 + 1], zrl[kg * 4 + 2], zrl[kg * 4 + 3]);
-                    const uint4 vih = make_uint4(zih[kg * 4], zih[kg * 4 + 1], zih[kg * 4 + 2], zih[kg * 4 + 3]);
-                    const uint4 vil = make_uint4(zil[kg * 4], zil[kg * 4 + 1], zil[kg * 4 + 2], zil[kg * 4 + 3]);
-                    const uint32_t sg = 0x80008000u;                  // sign flip of both packed halves
-                    const uint4 nrh = make_uint4(vrh.x ^ sg, vrh.y ^ sg, vrh.z ^ sg, vrh.w ^ sg);
-                    const uint4 nrl = make_uint4(vrl.x ^ sg, vrl.y ^ sg, vrl.z ^ sg, vrl.w ^ sg);
-                    uint8_t* d = dst + kg * 2048;
-                    *reinterpret_cast<uint4*>(d + 0 * kA2ArrBytes) = vrh;
-                    *reinterpret_cast<uint4*>(d + 1 * kA2ArrBytes) = vrl;
-                    *reinterpret_cast<uint4*>(d + 2 * kA2ArrBytes) = vih;
-                    *reinterpret_cast<uint4*>(d + 3 * kA2ArrBytes) = vil;
-                    *reinterpret_cast<uint4*>(d + 4 * kA2ArrBytes) = nrh;
-                    *reinterpret_cast<uint4*>(d + 5 * kA2ArrBytes) = nrl;
+                    uint4 h, l;
+                    uint8_t* d = dst + hb * 2048;
+                    split8(er, h, l);
+                    *reinterpret_cast<uint4*>(d + 0 * kA2ArrBytes) = h;
+                    *reinterpret_cast<uint4*>(d + 1 * kA2ArrBytes) = l;
+                    split8(ei, h, l);
+                    *reinterpret_cast<uint4*>(d + 2 * kA2ArrBytes) = h;
+                    *reinterpret_cast<uint4*>(d + 3 * kA2ArrBytes) = l;
+                    split8(orr, h, l);
+                    *reinterpret_cast<uint4*>(d + 4 * kA2ArrBytes) = h;
+                    *reinterpret_cast<uint4*>(d + 5 * kA2ArrBytes) = l;
+                    split8(oi, h, l);
+                    *reinterpret_cast<uint4*>(d + 6 * kA2ArrBytes) = h;
+                    *reinterpret_cast<uint4*>(d + 7 * kA2ArrBytes) = l;
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full2[s]);
+                if (lane == 0) mbar_arrive(&full2[cg]);
             }
 
             // ---------------------------------------------------------------- power spectrum / complex output
@@ -409,56 +501,63 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
             tc_fence_after();
             float2* spec_row = nullptr;
             if (MODE == 1) spec_row = prm.spec + (static_cast<long long>(clip) * prm.n_frames + t) * kBins;
+            const bool mirrored = (cg >= 2);                          // k2 = 2 j + par >= 64
 #pragma unroll 1
-            for (int cc = 0; cc < 4; ++cc) {
-                const int k2_0 = 64 * h + 16 * cc;
-                float re[16], im[16];
-                tmem_ld16(tlane + 256 + k2_0, re);
-                tmem_ld16(tlane + 384 + k2_0, im);
-                tmem_ld_wait();
+            for (int hb = 0; hb < 2; ++hb) {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const int k2 = k2_0 + i;
-                    const int k = k1 + 256 * k2;
-                    int bin = -1;
-                    float sgn = 1.f;
-                    if (k <= kNfft / 2) bin = k;
-                    else if (k1 >= 1) { bin = kNfft - k; sgn = -1.f; }       // Hermitian mirror (conjugate)
-                    if (bin >= 0) {
-                        if (MODE == 0) p_s[bin] = re[i] * re[i] + im[i] * im[i];
-                        else spec_row[bin] = make_float2(re[i], sgn * im[i]);
+                for (int par = 0; par < 2; ++par) {
+                    const int j0 = 16 * cg + 8 * hb;
+                    float re[8], im[8];
+                    tmem_ld8(tlane + 256 + 128 * par + j0, re);
+                    tmem_ld8(tlane + 256 + 128 * par + 64 + j0, im);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int k = k1 + 256 * (2 * (j0 + i) + par);
+                        int bin;
+                        float sgn = 1.f;
+                        if (!mirrored) bin = k;
+                        else if (k1 >= 1) { bin = kNfft - k; sgn = -1.f; }        // Hermitian mirror (conjugate)
+                        else bin = (k == kNfft / 2) ? k : -1;
+                        if (bin >= 0) {
+                            if (MODE == 0) p_s[bin] = re[i] * re[i] + im[i] * im[i];
+                            else spec_row[bin] = make_float2(re[i] * inv_scale, sgn * im[i] * inv_scale);
+                        }
                     }
                 }
             }
-            tc_fence_before();
-            worker_sync();                                            // v_s complete, TMEM reads done
             // row k1 = 128: X[128 + 256 k2] = sum_n2 Y[n2,128] exp(-2 pi i n2 (2 k2 + 1)/256), k2 in [0,64)
+            worker_sync();                                            // v_s (written by warps 0-3) visible
             {
-                const int k2 = tid >> 2;
-                const int part = tid & 3;
+                const int k2 = tid >> 3;
+                const int part = tid & 7;
                 float ar = 0.f, ai = 0.f;
-                const int m = 2 * k2 + 1;
+                const int mm = 2 * k2 + 1;
 #pragma unroll 8
-                for (int i = 0; i < 32; ++i) {
-                    const int n2 = part * 32 + i;
-                    const float2 w = cs_s[(n2 * m) & 255];
+                for (int i = 0; i < 16; ++i) {
+                    const int n2 = part * 16 + i;
+                    const float2 w = cs_s[(n2 * mm) & 255];
                     const float v = v_s[n2];
                     ar = fmaf(v, w.x, ar);
                     ai = fmaf(v, w.y, ai);
                 }
-                ar += __shfl_xor_sync(0xffffffffu, ar, 1);
-                ai += __shfl_xor_sync(0xffffffffu, ai, 1);
-                ar += __shfl_xor_sync(0xffffffffu, ar, 2);
-                ai += __shfl_xor_sync(0xffffffffu, ai, 2);
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    ar += __shfl_xor_sync(0xffffffffu, ar, o);
+                    ai += __shfl_xor_sync(0xffffffffu, ai, o);
+                }
                 if (part == 0) {
                     if (MODE == 0) p_s[128 + 256 * k2] = ar * ar + ai * ai;
-                    else spec_row[128 + 256 * k2] = make_float2(ar, ai);
+                    else spec_row[128 + 256 * k2] = make_float2(ar * inv_scale, ai * inv_scale);
                 }
             }
+            tc_fence_before();
             if (MODE == 0) {
+                if (tid < 3) p_s[kBins + tid] = 0.f;                  // padding read by the vectorised mel bands
                 worker_sync();                                        // power spectrum complete
                 float* out_row = prm.out + (static_cast<long long>(clip) * prm.n_frames + t) * kMel;
-                mel_db_from_smem(p_s, mel_tab_s, prm.mel_w, prm.norm, 1.0f, out_row, warp, lane);
+                mel_db_from_smem(p_s, mel_tab_s, prm.mel_w, prm.norm, inv_scale * inv_scale, out_row, warp, lane,
+                                 kWorkerWarps);
             }
             worker_sync();                                            // ring (aliased by p_s) may be refilled
             if (lane == 0) mbar_arrive(ring_free);
@@ -482,9 +581,10 @@ __global__ void __launch_bounds__(256) power_mel_db_kernel(const float2* __restr
                                                            const float* __restrict__ norm, float* __restrict__ out) {
     extern __shared__ __align__(128) uint8_t smem[];
     float* p_s = reinterpret_cast<float*>(smem);
-    int4* mel_tab_s = reinterpret_cast<int4*>(smem + ((kBins * 4 + 15) / 16) * 16);
+    int4* mel_tab_s = reinterpret_cast<int4*>(smem + ((kBins * 4 + 16 + 15) / 16) * 16);
     const int tid = threadIdx.x;
     for (int i = tid; i < kMel; i += 256) mel_tab_s[i] = mel_tab[i];
+    if (tid < 3) p_s[kBins + tid] = 0.f;
     for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
         const float2* x = spec + row * kBins;
         for (int k = tid; k < kBins; k += 256) {
@@ -492,7 +592,7 @@ __global__ void __launch_bounds__(256) power_mel_db_kernel(const float2* __restr
             p_s[k] = v.x * v.x + v.y * v.y;
         }
         __syncthreads();
-        mel_db_from_smem(p_s, mel_tab_s, mel_w, norm, 1.0f, out + row * kMel, tid >> 5, tid & 31);
+        mel_db_from_smem(p_s, mel_tab_s, mel_w, norm, 1.0f, out + row * kMel, tid >> 5, tid & 31, 8);
         __syncthreads();
     }
 }

@@ -44,6 +44,7 @@ struct sedb_ctx {
     int num_sms = 0;
     uint8_t* a1 = nullptr;        // stage-1 DFT constants
     uint8_t* b2 = nullptr;        // stage-2 DFT constants
+    float* hann = nullptr;        // padded Hann window
     float* mel_w = nullptr;       // compact mel weights
     int4* mel_tab = nullptr;      // per-filter band table
     // host-buffer pipeline state (sedb_logmel_host_f32 / sedb_sed_host_f32)
@@ -112,6 +113,9 @@ int sedb_create(sedb_ctx_t** out_ctx) {
     sedb_host::make_mel_bands(dense, SEDB_NUM_BINS, SEDB_MEL_BINS, tab, wts);
     CUDA_TRY(cudaMalloc(&c->a1, a1.size()));
     CUDA_TRY(cudaMalloc(&c->b2, b2.size()));
+    std::vector<float> hann = sedb_host::make_hann_padded(SEDB_FRAME_SIZE, SEDB_NFFT);
+    CUDA_TRY(cudaMalloc(&c->hann, hann.size() * sizeof(float)));
+    CUDA_TRY(cudaMemcpy(c->hann, hann.data(), hann.size() * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&c->mel_w, wts.size() * sizeof(float)));
     CUDA_TRY(cudaMalloc(&c->mel_tab, tab.size() * sizeof(int4)));
     CUDA_TRY(cudaMemcpy(c->a1, a1.data(), a1.size(), cudaMemcpyHostToDevice));
@@ -133,6 +137,7 @@ int sedb_destroy(sedb_ctx_t* c) {
     if (!c) return 0;
     cudaFree(c->a1);
     cudaFree(c->b2);
+    cudaFree(c->hann);
     cudaFree(c->mel_w);
     cudaFree(c->mel_tab);
     for (int i = 0; i < 2; ++i) {
@@ -153,9 +158,9 @@ int sedb_destroy(sedb_ctx_t* c) {
 static int launch_logmel(sedb_ctx_t* c, int mode, const float* wave, long long n_clips, long long n_samples,
                          long long wave_stride, const float* norm, float* out, float* spec, cudaStream_t st) {
     if (!c) return fail("null context");
-    if (!wave || (mode == 0 ? !out : !spec)) return fail("null buffer");
     if (n_clips < 0) return fail("negative clip count");
     if (n_clips == 0) return 0;
+    if (!wave || (mode == 0 ? !out : !spec)) return fail("null buffer");
     if (n_samples <= sedb::kPadRefl)
         return fail("n_samples=%lld: reflect padding (center=True, n_fft=%d) needs more than %d samples", n_samples,
                     SEDB_NFFT, sedb::kPadRefl);
@@ -169,6 +174,7 @@ static int launch_logmel(sedb_ctx_t* c, int mode, const float* wave, long long n
     p.n_frames = static_cast<int>(sedb_num_frames(n_samples));
     p.a1 = c->a1;
     p.b2 = c->b2;
+    p.hann = c->hann;
     p.mel_w = c->mel_w;
     p.mel_tab = c->mel_tab;
     p.norm = norm;
@@ -200,9 +206,9 @@ int sedb_stft_c64(sedb_ctx_t* ctx, const float* wave_dev, long long n_clips, lon
 int sedb_power_mel_db_f32(sedb_ctx_t* c, const float* spec_dev, long long rows, const float* norm_dev, float* out_dev,
                           void* stream) {
     if (!c) return fail("null context");
-    if (!spec_dev || !out_dev) return fail("null buffer");
     if (rows < 0) return fail("negative row count");
     if (rows == 0) return 0;
+    if (!spec_dev || !out_dev) return fail("null buffer");
     const int grid = static_cast<int>(rows < 4LL * c->num_sms ? rows : 4LL * c->num_sms);
     sedb::power_mel_db_kernel<<<grid, 256, 68 * 1024, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float2*>(spec_dev), rows, c->mel_w, c->mel_tab, norm_dev, out_dev);

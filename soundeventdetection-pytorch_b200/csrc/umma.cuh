@@ -146,7 +146,7 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // x ~= hi + lo with both halves in a 16-bit float format; three MMAs (hi*hi + lo*hi + hi*lo) then
 // reproduce the fp32 product to ~2^-17 (bf16) / ~2^-22 (fp16) relative.
 #ifndef SEDB_SPLIT_FP16
-#define SEDB_SPLIT_FP16 0
+#define SEDB_SPLIT_FP16 1
 #endif
 #if SEDB_SPLIT_FP16
 typedef __half split_t;

@@ -99,3 +99,73 @@ def factored_power_spectrum(g, rnd=None):
     P[128 + 256 * np.arange(64)] = np.abs(V) ** 2
     X[128 + 256 * np.arange(64)] = V
     return P, X
+
+
+# ---------------------------------------------------------------------------------------------------------
+# v2 dataflow: stage 1 with the even/odd fold over n1 (K = 128), stage 2 with one radix-2 DIF step over n2
+# (two 64-point complex DFT GEMMs sharing one constant matrix).
+#
+#   U[m,n2] = X[m,n2] + X[256-m,n2] (m=1..127), U[0] = X[0];  V[m,n2] = X[m,n2] - X[256-m,n2], V[0] = 0
+#   Dc[k1,n2] = sum_m cos(2 pi k1 m/256) U[m,n2] + (-1)^k1 X[128,n2]          (GEMM + CUDA-core correction)
+#   Ds[k1,n2] = sum_m -sin(2 pi k1 m/256) V[m,n2]
+#   Y128[n2]  = sum_m (-1)^m U[m,n2] + X[128,n2]                               (CUDA cores, producer side)
+#   Z = (Dc + i Ds) exp(-2 pi i k1 n2/32768)
+#   E[k1,n] = Z[k1,n] + Z[k1,n+64];   O[k1,n] = (Z[k1,n] - Z[k1,n+64]) exp(-2 pi i n/128)     n in [0,64)
+#   X[k1 + 256 (2j)]   = sum_n E[k1,n] exp(-2 pi i n j/64)
+#   X[k1 + 256 (2j+1)] = sum_n O[k1,n] exp(-2 pi i n j/64)
+def stage1_fold_constants():
+    k1 = np.arange(128)[:, None]
+    m = np.arange(128)[None, :]
+    ang = 2 * np.pi * ((k1 * m) % N1) / N1
+    return np.cos(ang), -np.sin(ang)
+
+
+def stage2_radix2_constants():
+    """B matrices [K = 64 (n), N = 128 (64 re | 64 im)] for the real and imaginary parts of the A operand."""
+    n = np.arange(64)[:, None]
+    j = np.arange(64)[None, :]
+    ang = 2 * np.pi * ((n * j) % 64) / 64
+    c, s = np.cos(ang), np.sin(ang)
+    b_re = np.concatenate([c, -s], axis=1)      # multiplies Er: re += Er c, im += -Er s
+    b_im = np.concatenate([s, c], axis=1)       # multiplies Ei: re += Ei s, im +=  Ei c
+    return b_re, b_im
+
+
+def factored_power_spectrum_v2(g, rnd=None, scale=1.0):
+    X1 = (np.asarray(g, dtype=np.float64) * scale).astype(np.float32).reshape(N1, N2)
+    U = X1[:128].copy()
+    V = np.zeros_like(U)
+    U[1:] = X1[1:128] + X1[255:128:-1]
+    V[1:] = X1[1:128] - X1[255:128:-1]
+    C, S = stage1_fold_constants()
+    sign_k1 = (-1.0) ** np.arange(128)[:, None]
+    Dc = mm3(C.astype(np.float32), U, rnd) + sign_k1 * X1[128][None, :].astype(np.float64)
+    Ds = mm3(S.astype(np.float32), V, rnd)
+    y128 = ((-1.0) ** np.arange(128)[:, None] * U.astype(np.float64)).sum(0) + X1[128]
+    k1 = np.arange(128)[:, None]
+    n2 = np.arange(N2)[None, :]
+    Z = (Dc + 1j * Ds) * np.exp(-2j * np.pi * (k1 * n2) / N)
+    E = Z[:, :64] + Z[:, 64:]
+    O = (Z[:, :64] - Z[:, 64:]) * np.exp(-2j * np.pi * np.arange(64)[None, :] / 128)
+    b_re, b_im = stage2_radix2_constants()
+    f32 = np.float32
+
+    def dft64(A):
+        D = mm3(A.real.astype(f32), b_re.astype(f32), rnd) + mm3(A.imag.astype(f32), b_im.astype(f32), rnd)
+        return D[:, :64] + 1j * D[:, 64:]
+
+    Xe, Xo = dft64(E), dft64(O)
+    X = np.zeros(N // 2 + 1, dtype=np.complex128)
+    for kk1 in range(128):
+        for j in range(64):
+            for par, val in ((0, Xe[kk1, j]), (1, Xo[kk1, j])):
+                k = kk1 + 256 * (2 * j + par)
+                if k <= N // 2:
+                    X[k] = val
+                elif kk1 >= 1:
+                    X[N - k] = np.conj(val)
+    kk2 = np.arange(64)[:, None]
+    nn2 = np.arange(N2)[None, :]
+    X[128 + 256 * np.arange(64)] = (y128[None, :] * np.exp(-2j * np.pi * ((nn2 * (2 * kk2 + 1)) % 256) / 256)).sum(1)
+    X = X / scale
+    return np.abs(X) ** 2, X
