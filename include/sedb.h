@@ -125,6 +125,9 @@ int sedb_sed_host_f32(sedb_ctx_t* ctx, sedb_cnn_t* cnn, const float* wave_host, 
  * stride; neg_b: set the B-negate bit. */
 int sedb_debug_umma_probe(const float* a_dev, const float* b_dev, float* d_dev, int N, int K, int a_major,
                           int b_major, int pad, int neg_b, int swap_lbo_sbo, void* stream);
+/* Per-phase cycle counters of logmel_fused_kernel (thread 0 of every CTA, summed): enable != 0 switches the
+ * instrumentation on; out_host16 (nullable) receives and clears the 16 counters; enable == 0 switches it off. */
+int sedb_debug_phase_profile(int enable, unsigned long long* out_host16);
 /* Number of kernel launches issued through this library since load (bench.py's gpu_launches). */
 long long sedb_launch_count(void);
 

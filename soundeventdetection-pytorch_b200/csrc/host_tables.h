@@ -133,32 +133,96 @@ inline std::vector<float> make_mel_matrix(int sr, int n_fft, int n_mels, double 
     return w;
 }
 
-struct MelBand {
-    int lo, cnt, woff, pad;
+// Per-filter line coefficients: weight(k) = max(0, min(a_r k + b_r, a_f k + b_f)), the triangle of
+// librosa.filters.mel with the Slaney area normalisation folded in (evaluated in fp32 by the kernels; agrees with the
+// float32 matrix to ~1e-6 of the peak weight).
+inline std::vector<float> make_mel_coefficients(int sr, int n_fft, int n_mels, double fmin, double fmax) {
+    std::vector<double> mel_f(n_mels + 2);
+    const double lo = hz_to_mel(fmin), hi = hz_to_mel(fmax);
+    const double step = (hi - lo) / (n_mels + 1);
+    for (int i = 0; i < n_mels + 2; ++i) mel_f[i] = mel_to_hz(i == n_mels + 1 ? hi : lo + step * i);
+    const double val = 1.0 / (static_cast<double>(n_fft) * (1.0 / sr));
+    std::vector<float> c(static_cast<size_t>(n_mels) * 4);
+    for (int i = 0; i < n_mels; ++i) {
+        const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+        const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+        c[4 * i + 0] = static_cast<float>(val * enorm / fd0);
+        c[4 * i + 1] = static_cast<float>(-mel_f[i] * enorm / fd0);
+        c[4 * i + 2] = static_cast<float>(-val * enorm / fd1);
+        c[4 * i + 3] = static_cast<float>(mel_f[i + 2] * enorm / fd1);
+    }
+    return c;
+}
+
+struct MelTabEntry {
+    int x, y, z, w;
 };
-// Compact band form: per filter the contiguous run of non-zero weights.
-inline void make_mel_bands(const std::vector<float>& dense, int n_bins, int n_mels, std::vector<MelBand>& tab,
-                           std::vector<float>& weights) {
-    tab.resize(n_mels);
+constexpr int kMelRows = 16;          // work rows (one per worker warp of the fused kernel)
+constexpr int kMelSegsPerRow = 16;
+constexpr int kMelTabEntries = kMelRows * kMelSegsPerRow + 64;
+
+// Compact, load-balanced form of the filterbank for the kernels:
+//   weights : per filter the contiguous run of non-zero weights, extended down to a multiple of 4 bins and padded
+//             to a multiple of 4 entries (float4 loads);
+//   tab[row*16 + s] = {first bin, filter index, float4 count, partial-sum slot}  -- segments of work row `row`
+//             (a filter may be split over consecutive rows; count 0 terminates a row);
+//   tab[256 + m]    = {first slot, number of slots, 0, 0} of filter m (partials are summed in slot order).
+inline bool make_mel_segments(const std::vector<float>& dense, int n_bins, int n_mels, std::vector<MelTabEntry>& tab,
+                              std::vector<float>& weights, int& n_slots) {
+    tab.assign(kMelTabEntries, MelTabEntry{0, 0, 0, 0});
     weights.clear();
+    std::vector<int> first(n_mels), n4(n_mels), woff(n_mels);
+    long long total_cost = 0;
+    auto cost = [](int items) { return (items + 31) / 32 + 2; };
     for (int m = 0; m < n_mels; ++m) {
-        int first = -1, last = -1;
+        int lo = -1, hi = -1;
         for (int k = 0; k < n_bins; ++k)
             if (dense[static_cast<size_t>(k) * n_mels + m] != 0.f) {
-                if (first < 0) first = k;
-                last = k;
+                if (lo < 0) lo = k;
+                hi = k;
             }
-        if (first < 0) { first = 0; last = -1; }
-        first &= ~3;                                            // bands start on a multiple of 4 bins (float4 loads)
-        int cnt = last - first + 1;
+        if (lo < 0) { lo = 0; hi = -1; }
+        lo &= ~3;
+        int cnt = hi - lo + 1;
         if (cnt < 0) cnt = 0;
         const int cnt_pad = (cnt + 3) & ~3;
-        tab[m] = {first, cnt_pad, static_cast<int>(weights.size()), 0};
+        first[m] = lo;
+        n4[m] = cnt_pad / 4;
+        woff[m] = static_cast<int>(weights.size());
         for (int i = 0; i < cnt_pad; ++i) {
-            const int k = first + i;
+            const int k = lo + i;
             weights.push_back(k < n_bins ? dense[static_cast<size_t>(k) * n_mels + m] : 0.f);
         }
+        total_cost += cost(n4[m]);
     }
+    const long long quota = (total_cost + kMelRows - 1) / kMelRows + 1;
+    int row = 0, seg = 0, slot = 0;
+    long long used = 0;
+    for (int m = 0; m < n_mels; ++m) {
+        int done = 0;
+        tab[kMelRows * kMelSegsPerRow + m] = MelTabEntry{slot, 0, 0, 0};
+        if (n4[m] == 0) continue;
+        while (done < n4[m]) {
+            if ((used >= quota || seg >= kMelSegsPerRow) && row + 1 < kMelRows) {
+                ++row;
+                seg = 0;
+                used = 0;
+            }
+            if (seg >= kMelSegsPerRow) return false;
+            long long room = (quota - used - 2) * 32;                 // float4 items that still fit this row
+            if (room < 32) room = 32;
+            int take = n4[m] - done;
+            if (take > room && row + 1 < kMelRows) take = static_cast<int>(room);
+            tab[row * kMelSegsPerRow + seg] = MelTabEntry{first[m] + 4 * done, m, take, slot};
+            tab[kMelRows * kMelSegsPerRow + m].y += 1;
+            used += cost(take);
+            done += take;
+            ++seg;
+            ++slot;
+        }
+    }
+    n_slots = slot;
+    return slot <= 128;
 }
 
 }  // namespace sedb_host

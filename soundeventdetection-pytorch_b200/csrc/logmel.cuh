@@ -53,8 +53,12 @@ constexpr int kOffAlt = kOffRing + kRingBytes;             // per-row alternatin
 constexpr int kOffX128 = kOffAlt + 16 * 128 * 4;           // X[128, n2]      128 floats
 constexpr int kOffV = kOffX128 + 512;                      // Y[n2,128]       128 floats
 constexpr int kOffCs = kOffV + 512;                        // exp(-2 pi i j/256) 256 float2
-constexpr int kOffMelTab = kOffCs + 2048;                  // 64 x int4 {lo, cnt, woff, 0}
-constexpr int kOffRed = kOffMelTab + 1024;                 // absmax reduction scratch (16 floats) + scale
+constexpr int kMelTabEntries = 16 * 16 + 64;               // host_tables.h: make_mel_segments
+constexpr int kOffMelTab = kOffCs + 2048;                  // segment table (320 x int4)
+constexpr int kOffMelPart = kOffMelTab + kMelTabEntries * 16;   // partial sums (128 floats)
+constexpr int kOffMelCoef = kOffMelPart + 512;             // 64 x float4 line coefficients
+constexpr int kOffNorm = kOffMelCoef + 1024;               // mean[64], std[64] (when given)
+constexpr int kOffRed = kOffNorm + 512;                    // absmax reduction scratch (16 floats) + scale
 constexpr int kOffBars = kOffRed + 128;                    // mbarriers
 constexpr int kOffTmem = kOffBars + 256;                   // tmem base address
 constexpr int kSmemBytes = kOffTmem + 16;
@@ -76,11 +80,12 @@ struct LogmelParams {
     const uint8_t* a1;        // stage-1 constants, 8 chunks x 16 KB, canonical K-major, split hi/lo
     const uint8_t* b2;        // stage-2 constants, 4 x 16 KB
     const float* hann;        // np.hanning(31680) centre-padded to 32768
-    const float* mel_w;       // compact mel weights (band of filter m starts at mel_tab[m].z)
-    const int4* mel_tab;      // 64 x {first bin (multiple of 4), padded count, weight offset, 0}
+    const float* mel_w;       // 64 x {a_r, b_r, a_f, b_f}: weight(k) = max(0, min(a_r k + b_r, a_f k + b_f))
+    const int4* mel_tab;      // balanced segment table + per-filter slot ranges (host_tables.h)
     const float* norm;        // nullable: mean[64] then std[64]  (SpectogramDataset.transform, logMel mode)
     float* out;               // MODE 0: [B, T, 64] fp32 log-mel
     float2* spec;             // MODE 1: [B, T, 16385] complex64 STFT
+    unsigned long long* prof; // nullable: per-phase cycle counters (diagnostics)
 };
 
 // named barrier among the worker threads only
@@ -108,6 +113,20 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void split4(const float* x, uint2& hi, uint2& lo) {
+    split_pack2(x[0], x[1], hi.x, lo.x);
+    split_pack2(x[2], x[3], hi.y, lo.y);
+}
+
 // split 8 floats into packed hi / lo halves (16 B each)
 __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
     uint32_t h[4], l[4];
@@ -117,40 +136,62 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// Banded mel dot products over a power spectrum in shared memory, then dB (+ optional normalisation).
-// Called by `nwarps` warps; warp w owns filters w, w+nwarps, ...  Bands start on multiples of 4 bins.
-__device__ __forceinline__ void mel_db_from_smem(const float* __restrict__ p_s, const int4* __restrict__ mel_tab_s,
-                                                 const float* __restrict__ mel_w, const float* __restrict__ norm,
-                                                 float inv_scale2, float* __restrict__ out_row, int warp, int lane,
-                                                 int nwarps) {
-    float mine = 0.f;
-    const int per_warp = kMel / nwarps;
+// Banded mel dot products over a power spectrum in shared memory.  The 64 filters are cut into load-balanced
+// segments (16 work rows); every segment's partial sum goes to a fixed slot and the slots of a filter are added in
+// slot order, so the result does not depend on scheduling.  Called by `nwarps` warps, followed by a block-level
+// barrier and mel_finalize().
+__device__ __forceinline__ void mel_partials(const float* __restrict__ p_s, const int4* __restrict__ tab_s,
+                                             const float* __restrict__ mel_w, float* __restrict__ part_s, int warp,
+                                             int lane, int nwarps) {
+    for (int row = warp; row < 16; row += nwarps) {
 #pragma unroll 1
-    for (int i = 0; i < per_warp; ++i) {
-        const int m = warp + i * nwarps;
-        const int4 tab = mel_tab_s[m];
-        const float4* w = reinterpret_cast<const float4*>(mel_w + tab.z);
-        const float4* p = reinterpret_cast<const float4*>(p_s + tab.x);
-        float acc = 0.f;
-        for (int j = lane; j < (tab.y >> 2); j += 32) {
-            const float4 pv = p[j];
-            const float4 wv = __ldg(w + j);
-            acc = fmaf(pv.x, wv.x, acc);
-            acc = fmaf(pv.y, wv.y, acc);
-            acc = fmaf(pv.z, wv.z, acc);
-            acc = fmaf(pv.w, wv.w, acc);
-        }
+        for (int sg = 0; sg < 16; ++sg) {
+            const int4 e = tab_s[row * 16 + sg];
+            if (e.z == 0) break;
+            const float4 cf = reinterpret_cast<const float4*>(mel_w)[e.y];
+            const float4* p = reinterpret_cast<const float4*>(p_s + e.x);
+            float acc0 = 0.f, acc1 = 0.f;
+            for (int j = lane; j < e.z; j += 32) {
+                const float4 pv = p[j];
+                const float k = static_cast<float>(e.x + 4 * j);
+                const float r0 = fmaf(cf.x, k, cf.y), f0 = fmaf(cf.z, k, cf.w);
+                const float r1 = r0 + cf.x, f1 = f0 + cf.z;
+                const float r2 = r1 + cf.x, f2 = f1 + cf.z;
+                const float r3 = r2 + cf.x, f3 = f2 + cf.z;
+                acc0 = fmaf(pv.x, fmaxf(0.f, fminf(r0, f0)), acc0);
+                acc1 = fmaf(pv.y, fmaxf(0.f, fminf(r1, f1)), acc1);
+                acc0 = fmaf(pv.z, fmaxf(0.f, fminf(r2, f2)), acc0);
+                acc1 = fmaf(pv.w, fmaxf(0.f, fminf(r3, f3)), acc1);
+            }
+            float acc = acc0 + acc1;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == i) mine = acc;
-    }
-    if (lane < per_warp) {
-        const int m = warp + lane * nwarps;
-        float db = 10.0f * log10f(fmaxf(1e-10f, mine * inv_scale2));     // librosa.power_to_db(ref=1, amin=1e-10)
-        if (norm != nullptr) db = (db - norm[m]) / norm[kMel + m];       // spectograms_dataset.py:105
-        out_row[m] = db;
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) part_s[e.w] = acc;
+        }
     }
 }
+// threads 0..63: sum the partial slots of filter `tid`, convert to dB, normalise, store.
+__device__ __forceinline__ void mel_finalize(const float* __restrict__ part_s, const int4* __restrict__ tab_s,
+                                             const float* __restrict__ norm, float inv_scale2,
+                                             float* __restrict__ out_row, int tid) {
+    if (tid < kMel) {
+        const int4 f = tab_s[256 + tid];
+        float a = 0.f;
+        for (int i = 0; i < f.y; ++i) a += part_s[f.x + i];
+        float db = 10.0f * log10f(fmaxf(1e-10f, a * inv_scale2));        // librosa.power_to_db(ref=1, amin=1e-10)
+        if (norm != nullptr) db = (db - norm[tid]) / norm[kMel + tid];   // spectograms_dataset.py:105
+        out_row[tid] = db;
+    }
+}
+
+#define SEDB_PROF(i)                                                             \
+    do {                                                                         \
+        if (prm.prof != nullptr && tid == 0) {                                   \
+            const long long now__ = clock64();                                   \
+            atomicAdd(prm.prof + (i), static_cast<unsigned long long>(now__ - tprev)); \
+            tprev = now__;                                                       \
+        }                                                                        \
+    } while (0)
 
 template <int MODE>   // 0: log-mel output; 1: complex STFT output
 __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelParams prm) {
@@ -163,6 +204,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
     float* v_s = reinterpret_cast<float*>(smem + kOffV);
     float2* cs_s = reinterpret_cast<float2*>(smem + kOffCs);
     int4* mel_tab_s = reinterpret_cast<int4*>(smem + kOffMelTab);
+    float* part_s = reinterpret_cast<float*>(smem + kOffMelPart);
+    float* coef_s = reinterpret_cast<float*>(smem + kOffMelCoef);
+    float* norm_s = reinterpret_cast<float*>(smem + kOffNorm);
     float* red_s = reinterpret_cast<float*>(smem + kOffRed);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + kOffTmem);
@@ -183,7 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         for (int s = 0; s < kNumSlots; ++s) {
             mbar_init(&full1[s], kWorkerWarps + 1);
             mbar_init(&empty1[s], 1);
-            mbar_init(&full2[s], 4);
+            mbar_init(&full2[s], kWorkerWarps);
         }
         mbar_init(d1_full, 1);
         mbar_init(d2_full, 1);
@@ -197,7 +241,10 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         sincospif(static_cast<float>(i) * (1.0f / 128.0f), &s, &c);      // exp(-2 pi i j/256) = (c, -s)
         cs_s[i] = make_float2(c, -s);
     }
-    for (int i = tid; i < kMel; i += kThreads) mel_tab_s[i] = prm.mel_tab[i];
+    for (int i = tid; i < kMelTabEntries; i += kThreads) mel_tab_s[i] = prm.mel_tab[i];
+    for (int i = tid; i < 4 * kMel; i += kThreads) coef_s[i] = prm.mel_w[i];
+    if (prm.norm != nullptr)
+        for (int i = tid; i < 2 * kMel; i += kThreads) norm_s[i] = prm.norm[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -306,26 +353,21 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
     // ======================================================================== 16 worker warps
     else {
         const int q = warp & 3;                 // TMEM lane quarter
-        const int cg = warp >> 2;               // column group: n in [16 cg, 16 cg + 16) (and + 64)
+        const int sub = warp >> 2;              // which 4 of a chunk's 16 columns (stage-2 operand), which 16 of 64 (output)
         const int k1 = q * 32 + lane;           // this thread's stage-1 output row / stage-2 A row
         const uint32_t tlane = tmem + (static_cast<uint32_t>(q * 32) << 16);
         const float sgn_k1 = (k1 & 1) ? -1.f : 1.f;
 
-        // per-thread twiddle constants: W^j (j=1..3), W^4, anchors W^(16 cg + 8 hb), W^64; W = exp(-2 pi i k1/32768)
-        float2 wj[4], w4, anc[2], w64;
+        // per-thread twiddle constants, W = exp(-2 pi i k1/32768): W^j (j=1..3), anchors W^(16 c + 4 sub), W^64
+        float2 wj[4], anc[4], w64;
         {
             float s, c;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 sincospif(static_cast<float>(k1 * j) * (1.0f / 16384.0f), &s, &c);
                 wj[j] = make_float2(c, -s);
-            }
-            sincospif(static_cast<float>(k1 * 4) * (1.0f / 16384.0f), &s, &c);
-            w4 = make_float2(c, -s);
-#pragma unroll
-            for (int hb = 0; hb < 2; ++hb) {
-                sincospif(static_cast<float>(k1 * (16 * cg + 8 * hb)) * (1.0f / 16384.0f), &s, &c);
-                anc[hb] = make_float2(c, -s);
+                sincospif(static_cast<float>(k1 * (16 * j + 4 * sub)) * (1.0f / 16384.0f), &s, &c);
+                anc[j] = make_float2(c, -s);
             }
             sincospif(static_cast<float>(k1 * 64) * (1.0f / 16384.0f), &s, &c);
             w64 = make_float2(c, -s);
@@ -336,6 +378,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         const uint32_t b1_off = kA1ChunkBytes + (lane >> 1) * kB1Sbo + (r >> 3) * kB1Lbo + (r & 7) * 16 + (lane & 1) * 8;
         const float alt_sign = (r & 1) ? -1.f : 1.f;
 
+        long long tprev = clock64();
         for (int it = 0; it < n_iter; ++it) {
             const long long f = blockIdx.x + static_cast<long long>(it) * gridDim.x;
             const int clip = static_cast<int>(f / prm.n_frames);
@@ -390,17 +433,22 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 inv_scale = __uint_as_float(static_cast<uint32_t>(127 - e) << 23);
             }
 #endif
+            SEDB_PROF(0);   // frame load (+ block scale)
             // ---------------------------------------------------------------- stage 1: window, fold, split
             float alt[4] = {0.f, 0.f, 0.f, 0.f};
+            auto hann4 = [&](int row) { return __ldg(reinterpret_cast<const float4*>(prm.hann + 128 * row + 4 * lane)); };
+            float4 wa_n = hann4(r), wb_n = hann4(r == 0 ? 128 : 256 - r);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const int g = it * 8 + c;
                 const int s = g % kNumSlots;
                 const int u = g / kNumSlots;
                 const int m = 16 * c + r;
-                const int mb = (m == 0) ? 128 : 256 - m;
-                const float4 wa = __ldg(reinterpret_cast<const float4*>(prm.hann + 128 * m + 4 * lane));
-                const float4 wb = __ldg(reinterpret_cast<const float4*>(prm.hann + 128 * mb + 4 * lane));
+                const float4 wa = wa_n, wb = wb_n;
+                if (c + 1 < 8) {                                  // window values of the next chunk (L2) in flight
+                    wa_n = hann4(m + 16);
+                    wb_n = hann4(256 - (m + 16));
+                }
                 const float a0 = xa[c].x * wa.x * scale, a1 = xa[c].y * wa.y * scale;
                 const float a2 = xa[c].z * wa.z * scale, a3 = xa[c].w * wa.w * scale;
                 const float b0 = xb[c].x * wb.x * scale, b1 = xb[c].y * wb.y * scale;
@@ -435,9 +483,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
             *reinterpret_cast<float4*>(alt_s + r * 128 + 4 * lane) =
                 make_float4(alt_sign * alt[0], alt_sign * alt[1], alt_sign * alt[2], alt_sign * alt[3]);
 
+            SEDB_PROF(1);   // fold / split / store
             // ---------------------------------------------------------------- twiddle, radix-2, stage-2 A operand
             mbar_wait(d1_full, it & 1);
             tc_fence_after();
+            SEDB_PROF(2);   // wait for stage-1 MMAs
             worker_sync();                                            // x128_s / alt_s visible to all workers
             if (tid < 128) {
                 float acc = x128_s[tid];
@@ -445,68 +495,63 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 for (int rr = 0; rr < 16; ++rr) acc += alt_s[rr * 128 + tid];
                 v_s[tid] = acc;                                       // Y[n2,128] (scaled)
             }
-            {
-                uint8_t* dst = ring + cg * kSlotBytes + k1 * 16;
 #pragma unroll 1
-                for (int hb = 0; hb < 2; ++hb) {
-                    const int n0 = 16 * cg + 8 * hb;
-                    float c0[8], c1[8], s0[8], s1[8];
-                    tmem_ld8(tlane + n0, c0);
-                    tmem_ld8(tlane + 64 + n0, c1);
-                    tmem_ld8(tlane + 128 + n0, s0);
-                    tmem_ld8(tlane + 192 + n0, s1);
-                    tmem_ld_wait();
-                    float er[8], ei[8], orr[8], oi[8];
+            for (int c = 0; c < 4; ++c) {
+                // chunk c = columns n in [16 c, 16 c + 16) (and n + 64); this warp owns n0 .. n0 + 3
+                const int n0 = 16 * c + 4 * sub;
+                float c0[4], c1[4], s0[4], s1[4];
+                tmem_ld4(tlane + n0, c0);
+                tmem_ld4(tlane + 64 + n0, c1);
+                tmem_ld4(tlane + 128 + n0, s0);
+                tmem_ld4(tlane + 192 + n0, s1);
+                tmem_ld_wait();
+                float er[4], ei[4], orr[4], oi[4];
 #pragma unroll
-                    for (int i4 = 0; i4 < 2; ++i4) {
-                        const float2 tb = (i4 == 0) ? anc[hb] : cmul(anc[hb], w4);
-#pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) {
-                            const int i = 4 * i4 + jj;
-                            const float2 tw0 = (jj == 0) ? tb : cmul(tb, wj[jj]);
-                            const float2 tw1 = cmul(tw0, w64);
-                            const float yr0 = fmaf(sgn_k1, x128_s[n0 + i], c0[i]);
-                            const float yr1 = fmaf(sgn_k1, x128_s[64 + n0 + i], c1[i]);
-                            const float2 z0 = cmul(make_float2(yr0, s0[i]), tw0);
-                            const float2 z1 = cmul(make_float2(yr1, s1[i]), tw1);
-                            er[i] = z0.x + z1.x;
-                            ei[i] = z0.y + z1.y;
-                            const float2 o = cmul(make_float2(z0.x - z1.x, z0.y - z1.y), cs_s[2 * (n0 + i)]);
-                            orr[i] = o.x;
-                            oi[i] = o.y;
-                        }
-                    }
-                    uint4 h, l;
-                    uint8_t* d = dst + hb * 2048;
-                    split8(er, h, l);
-                    *reinterpret_cast<uint4*>(d + 0 * kA2ArrBytes) = h;
-                    *reinterpret_cast<uint4*>(d + 1 * kA2ArrBytes) = l;
-                    split8(ei, h, l);
-                    *reinterpret_cast<uint4*>(d + 2 * kA2ArrBytes) = h;
-                    *reinterpret_cast<uint4*>(d + 3 * kA2ArrBytes) = l;
-                    split8(orr, h, l);
-                    *reinterpret_cast<uint4*>(d + 4 * kA2ArrBytes) = h;
-                    *reinterpret_cast<uint4*>(d + 5 * kA2ArrBytes) = l;
-                    split8(oi, h, l);
-                    *reinterpret_cast<uint4*>(d + 6 * kA2ArrBytes) = h;
-                    *reinterpret_cast<uint4*>(d + 7 * kA2ArrBytes) = l;
+                for (int jj = 0; jj < 4; ++jj) {
+                    const float2 tw0 = (jj == 0) ? anc[c] : cmul(anc[c], wj[jj]);
+                    const float2 tw1 = cmul(tw0, w64);
+                    const float yr0 = fmaf(sgn_k1, x128_s[n0 + jj], c0[jj]);
+                    const float yr1 = fmaf(sgn_k1, x128_s[64 + n0 + jj], c1[jj]);
+                    const float2 z0 = cmul(make_float2(yr0, s0[jj]), tw0);
+                    const float2 z1 = cmul(make_float2(yr1, s1[jj]), tw1);
+                    er[jj] = z0.x + z1.x;
+                    ei[jj] = z0.y + z1.y;
+                    const float2 o = cmul(make_float2(z0.x - z1.x, z0.y - z1.y), cs_s[2 * (n0 + jj)]);
+                    orr[jj] = o.x;
+                    oi[jj] = o.y;
                 }
+                // K-major A operand: row k1, K index 4 sub + jj -> K-group sub/2, byte (sub&1)*8 inside the 16-B row
+                uint8_t* d = ring + c * kSlotBytes + (sub >> 1) * 2048 + k1 * 16 + (sub & 1) * 8;
+                uint2 h, l;
+                split4(er, h, l);
+                *reinterpret_cast<uint2*>(d + 0 * kA2ArrBytes) = h;
+                *reinterpret_cast<uint2*>(d + 1 * kA2ArrBytes) = l;
+                split4(ei, h, l);
+                *reinterpret_cast<uint2*>(d + 2 * kA2ArrBytes) = h;
+                *reinterpret_cast<uint2*>(d + 3 * kA2ArrBytes) = l;
+                split4(orr, h, l);
+                *reinterpret_cast<uint2*>(d + 4 * kA2ArrBytes) = h;
+                *reinterpret_cast<uint2*>(d + 5 * kA2ArrBytes) = l;
+                split4(oi, h, l);
+                *reinterpret_cast<uint2*>(d + 6 * kA2ArrBytes) = h;
+                *reinterpret_cast<uint2*>(d + 7 * kA2ArrBytes) = l;
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&full2[cg]);
+                if (lane == 0) mbar_arrive(&full2[c]);
             }
-
+            SEDB_PROF(3);   // twiddle / radix-2 / split
             // ---------------------------------------------------------------- power spectrum / complex output
             mbar_wait(d2_full, it & 1);
             tc_fence_after();
+            SEDB_PROF(4);   // wait for stage-2 MMAs
             float2* spec_row = nullptr;
             if (MODE == 1) spec_row = prm.spec + (static_cast<long long>(clip) * prm.n_frames + t) * kBins;
-            const bool mirrored = (cg >= 2);                          // k2 = 2 j + par >= 64
+            const bool mirrored = (sub >= 2);                         // k2 = 2 j + par >= 64
 #pragma unroll 1
             for (int hb = 0; hb < 2; ++hb) {
 #pragma unroll
                 for (int par = 0; par < 2; ++par) {
-                    const int j0 = 16 * cg + 8 * hb;
+                    const int j0 = 16 * sub + 8 * hb;
                     float re[8], im[8];
                     tmem_ld8(tlane + 256 + 128 * par + j0, re);
                     tmem_ld8(tlane + 256 + 128 * par + 64 + j0, im);
@@ -526,6 +571,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                     }
                 }
             }
+            SEDB_PROF(5);   // power spectrum
             // row k1 = 128: X[128 + 256 k2] = sum_n2 Y[n2,128] exp(-2 pi i n2 (2 k2 + 1)/256), k2 in [0,64)
             worker_sync();                                            // v_s (written by warps 0-3) visible
             {
@@ -535,7 +581,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 const int mm = 2 * k2 + 1;
 #pragma unroll 8
                 for (int i = 0; i < 16; ++i) {
-                    const int n2 = part * 16 + i;
+                    const int n2 = part + 8 * i;                      // interleaved: table reads spread over banks
                     const float2 w = cs_s[(n2 * mm) & 255];
                     const float v = v_s[n2];
                     ar = fmaf(v, w.x, ar);
@@ -551,15 +597,22 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                     else spec_row[128 + 256 * k2] = make_float2(ar * inv_scale, ai * inv_scale);
                 }
             }
+            SEDB_PROF(6);   // row 128
             tc_fence_before();
             if (MODE == 0) {
                 if (tid < 3) p_s[kBins + tid] = 0.f;                  // padding read by the vectorised mel bands
                 worker_sync();                                        // power spectrum complete
+                SEDB_PROF(8);
+                mel_partials(p_s, mel_tab_s, coef_s, part_s, warp, lane, kWorkerWarps);
+                SEDB_PROF(9);
+                worker_sync();
+                SEDB_PROF(10);
                 float* out_row = prm.out + (static_cast<long long>(clip) * prm.n_frames + t) * kMel;
-                mel_db_from_smem(p_s, mel_tab_s, prm.mel_w, prm.norm, inv_scale * inv_scale, out_row, warp, lane,
-                                 kWorkerWarps);
+                mel_finalize(part_s, mel_tab_s, prm.norm != nullptr ? norm_s : nullptr, inv_scale * inv_scale, out_row, tid);
+                SEDB_PROF(11);
             }
             worker_sync();                                            // ring (aliased by p_s) may be refilled
+            SEDB_PROF(7);   // mel + dB
             if (lane == 0) mbar_arrive(ring_free);
         }
     }
@@ -582,8 +635,11 @@ __global__ void __launch_bounds__(256) power_mel_db_kernel(const float2* __restr
     extern __shared__ __align__(128) uint8_t smem[];
     float* p_s = reinterpret_cast<float*>(smem);
     int4* mel_tab_s = reinterpret_cast<int4*>(smem + ((kBins * 4 + 16 + 15) / 16) * 16);
+    float* part_s = reinterpret_cast<float*>(mel_tab_s + kMelTabEntries);
+    float* coef_s = part_s + 128;
     const int tid = threadIdx.x;
-    for (int i = tid; i < kMel; i += 256) mel_tab_s[i] = mel_tab[i];
+    for (int i = tid; i < kMelTabEntries; i += 256) mel_tab_s[i] = mel_tab[i];
+    for (int i = tid; i < 4 * kMel; i += 256) coef_s[i] = mel_w[i];
     if (tid < 3) p_s[kBins + tid] = 0.f;
     for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
         const float2* x = spec + row * kBins;
@@ -592,7 +648,9 @@ __global__ void __launch_bounds__(256) power_mel_db_kernel(const float2* __restr
             p_s[k] = v.x * v.x + v.y * v.y;
         }
         __syncthreads();
-        mel_db_from_smem(p_s, mel_tab_s, mel_w, norm, 1.0f, out + row * kMel, tid >> 5, tid & 31, 8);
+        mel_partials(p_s, mel_tab_s, coef_s, part_s, tid >> 5, tid & 31, 8);
+        __syncthreads();
+        mel_finalize(part_s, mel_tab_s, norm, 1.0f, out + row * kMel, tid);
         __syncthreads();
     }
 }

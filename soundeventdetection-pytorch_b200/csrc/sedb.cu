@@ -19,6 +19,7 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+unsigned long long* g_prof = nullptr;   // device buffer of 16 counters when phase profiling is enabled
 
 int fail(const char* fmt, ...) {
     char buf[512];
@@ -45,7 +46,7 @@ struct sedb_ctx {
     uint8_t* a1 = nullptr;        // stage-1 DFT constants
     uint8_t* b2 = nullptr;        // stage-2 DFT constants
     float* hann = nullptr;        // padded Hann window
-    float* mel_w = nullptr;       // compact mel weights
+    float* mel_w = nullptr;       // per-filter line coefficients {a_r, b_r, a_f, b_f}
     int4* mel_tab = nullptr;      // per-filter band table
     // host-buffer pipeline state (sedb_logmel_host_f32 / sedb_sed_host_f32)
     cudaStream_t s_copy = nullptr, s_comp = nullptr;
@@ -108,9 +109,12 @@ int sedb_create(sedb_ctx_t** out_ctx) {
     std::vector<uint8_t> b2 = sedb_host::make_stage2_constants(kFp16);
     std::vector<float> dense = sedb_host::make_mel_matrix(SEDB_SAMPLE_RATE, SEDB_NFFT, SEDB_MEL_BINS, SEDB_MEL_FMIN,
                                                           SEDB_MEL_FMAX);
-    std::vector<sedb_host::MelBand> tab;
+    std::vector<sedb_host::MelTabEntry> tab;
     std::vector<float> wts;
-    sedb_host::make_mel_bands(dense, SEDB_NUM_BINS, SEDB_MEL_BINS, tab, wts);
+    int mel_slots = 0;
+    if (!sedb_host::make_mel_segments(dense, SEDB_NUM_BINS, SEDB_MEL_BINS, tab, wts, mel_slots))
+        return fail("sedb_create: mel work table does not fit");
+    wts = sedb_host::make_mel_coefficients(SEDB_SAMPLE_RATE, SEDB_NFFT, SEDB_MEL_BINS, SEDB_MEL_FMIN, SEDB_MEL_FMAX);
     CUDA_TRY(cudaMalloc(&c->a1, a1.size()));
     CUDA_TRY(cudaMalloc(&c->b2, b2.size()));
     std::vector<float> hann = sedb_host::make_hann_padded(SEDB_FRAME_SIZE, SEDB_NFFT);
@@ -127,7 +131,7 @@ int sedb_create(sedb_ctx_t** out_ctx) {
     CUDA_TRY(cudaFuncSetAttribute(sedb::logmel_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   sedb::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(sedb::power_mel_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  68 * 1024));
+                                  72 * 1024));
     if (int rc = sedb_cnn_kernels_init()) return rc;
     *out_ctx = c;
     return 0;
@@ -180,6 +184,7 @@ static int launch_logmel(sedb_ctx_t* c, int mode, const float* wave, long long n
     p.norm = norm;
     p.out = out;
     p.spec = reinterpret_cast<float2*>(spec);
+    p.prof = g_prof;
     const long long total = n_clips * p.n_frames;
     const int grid = static_cast<int>(total < c->num_sms ? total : c->num_sms);
     if (mode == 0)
@@ -210,7 +215,7 @@ int sedb_power_mel_db_f32(sedb_ctx_t* c, const float* spec_dev, long long rows, 
     if (rows == 0) return 0;
     if (!spec_dev || !out_dev) return fail("null buffer");
     const int grid = static_cast<int>(rows < 4LL * c->num_sms ? rows : 4LL * c->num_sms);
-    sedb::power_mel_db_kernel<<<grid, 256, 68 * 1024, static_cast<cudaStream_t>(stream)>>>(
+    sedb::power_mel_db_kernel<<<grid, 256, 72 * 1024, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float2*>(spec_dev), rows, c->mel_w, c->mel_tab, norm_dev, out_dev);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
@@ -304,6 +309,23 @@ int sedb_sed_host_f32(sedb_ctx_t* ctx, sedb_cnn_t* cnn, const float* wave_host, 
                       long long n_samples, long long wave_stride, const float* norm_host, float* probs_host) {
     if (!cnn) return fail("null cnn handle");
     return run_host_pipeline(ctx, cnn, wave_host, n_clips, n_samples, wave_stride, norm_host, probs_host);
+}
+
+int sedb_debug_phase_profile(int enable, unsigned long long* out_host16) {
+    if (enable && !g_prof) {
+        CUDA_TRY(cudaMalloc(&g_prof, 16 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemset(g_prof, 0, 16 * sizeof(unsigned long long)));
+    }
+    if (out_host16 && g_prof) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        CUDA_TRY(cudaMemcpy(out_host16, g_prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemset(g_prof, 0, 16 * sizeof(unsigned long long)));
+    }
+    if (!enable && g_prof) {
+        cudaFree(g_prof);
+        g_prof = nullptr;
+    }
+    return 0;
 }
 
 int sedb_debug_umma_probe(const float* a_dev, const float* b_dev, float* d_dev, int N, int K, int a_major,

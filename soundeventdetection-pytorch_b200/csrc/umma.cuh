@@ -48,16 +48,35 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must not hang the GPU box.  On timeout (~seconds) the kernel traps,
-// which surfaces as a CUDA launch failure on the host instead of a wedged device.
+// try_wait with a suspend-time hint: the thread sleeps in hardware (no issue slots consumed) until the phase
+// completes or ~hint_ns elapsed, instead of polling.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU box.  On timeout (~seconds) the kernel traps, which surfaces
+// as a CUDA launch failure on the host instead of a wedged device.  The timeout clock is only consulted every 256
+// failed (sleeping) probes so that waiting warps do not steal issue slots from working ones.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    long long t0 = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
-            printf("sedb: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
-                   smem_u32(bar), parity);
-            __trap();
+    uint32_t spins = 0;
+    long long t0 = 0;
+    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+        if ((++spins & 0xffu) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 6000000000LL) {
+                printf("sedb: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
+                       smem_u32(bar), parity);
+                __trap();
+            }
         }
     }
 }
@@ -165,12 +184,24 @@ __device__ __forceinline__ uint32_t pack2(split_t a, split_t b) {
     uint16_t ub = *reinterpret_cast<uint16_t*>(&b);
     return static_cast<uint32_t>(ua) | (static_cast<uint32_t>(ub) << 16);
 }
-// split two floats, return packed hi pair and lo pair
+// Split two floats into packed hi and lo halves.  hi = x truncated to the 16-bit format's mantissa (a mask, exactly
+// representable, so its packed conversion is exact); lo = rn16(x - hi).  hi + lo reproduces x to ~2^-21 (fp16) /
+// ~2^-16 (bf16) relative.  Two packed conversions per pair instead of six scalar ones (conversions are a slow pipe).
 __device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
-    split_t h0 = to_split(x0), h1 = to_split(x1);
-    split_t l0 = to_split(x0 - from_split(h0)), l1 = to_split(x1 - from_split(h1));
-    hi = pack2(h0, h1);
-    lo = pack2(l0, l1);
+#if SEDB_SPLIT_FP16
+    const float h0 = __uint_as_float(__float_as_uint(x0) & 0xFFFFE000u);
+    const float h1 = __uint_as_float(__float_as_uint(x1) & 0xFFFFE000u);
+    const __half2 hh = __floats2half2_rn(h0, h1);
+    const __half2 ll = __floats2half2_rn(x0 - h0, x1 - h1);
+    hi = *reinterpret_cast<const uint32_t*>(&hh);
+    lo = *reinterpret_cast<const uint32_t*>(&ll);
+#else
+    const uint32_t u0 = __float_as_uint(x0), u1 = __float_as_uint(x1);
+    hi = __byte_perm(u0, u1, 0x7632);                          // {x0[31:16], x1[31:16]}: bf16 truncation, no cvt
+    const float h0 = __uint_as_float(u0 & 0xFFFF0000u), h1 = __uint_as_float(u1 & 0xFFFF0000u);
+    const __nv_bfloat162 ll = __floats2bfloat162_rn(x0 - h0, x1 - h1);
+    lo = *reinterpret_cast<const uint32_t*>(&ll);
+#endif
 }
 
 }  // namespace sedb
