@@ -51,39 +51,56 @@ def measured_peaks():
     return 6650.0, 1400.0, "fallback"
 
 
-class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons for one GPU while the timed region runs."""
+class ClockSampler:
+    """Streams nvidia-smi clocks / throttle reasons for one GPU (one background process, 50 ms period) and keeps the
+    samples taken between mark_start() and stop(): the timed region."""
 
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self._halt = index, [], threading.Event()
+        self.rows, self.t0, self.proc = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-i", str(index), "-lms", "50"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
 
-    def run(self):
-        while not self._halt.is_set():
-            try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([c.strip() for c in out.strip().split(",")])
-            except Exception:
-                pass
-            self._halt.wait(0.2)
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.strip().split(",")]))
+
+    def mark_start(self):
+        self.t0 = time.perf_counter()
 
     def stop(self):
-        self._halt.set()
-        self.join(timeout=3)
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        t1 = time.perf_counter()
+        time.sleep(0.12)
+        if self.proc is not None:
+            self.proc.terminate()
+        rows = [r for (ts, r) in self.rows if self.t0 is not None and self.t0 - 0.06 <= ts <= t1 + 0.12]
+        if not rows:
+            rows = [r for (_, r) in self.rows[-3:]]
+
+        def num(x):
+            try:
+                return float(x)
+            except Exception:
+                return None
+        sm = sorted(v for v in (num(r[0]) for r in rows if r) if v is not None)
+        mx = [v for v in (num(r[1]) for r in rows if len(r) > 1) if v is not None]
+        pw = [v for v in (num(r[2]) for r in rows if len(r) > 2) if v is not None]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v == "Active":
                     reasons.add(name)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 # ------------------------------------------------------------------------------------------------- CPU baseline
@@ -179,6 +196,7 @@ def run_ours(args):
     from sed_b200.dataset.spectogram import preprocess as P
     import refmodels
 
+    os.environ["NCCL_DEBUG"] = os.environ.get("SEDB_NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
     rank, local_rank, world = parallel.init_process_group("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
@@ -212,12 +230,12 @@ def run_ours(args):
             cnn_t.append((e1, e2))
         return probs
 
+    sampler = ClockSampler(local_rank)
     for _ in range(args.warmup):
         step(False)
     torch.cuda.synchronize()
     parallel.barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    sampler.mark_start()
     launches0 = lib.sedb_launch_count()
     t0, t1 = ev(), ev()
     torch.cuda.synchronize()

@@ -133,96 +133,68 @@ inline std::vector<float> make_mel_matrix(int sr, int n_fft, int n_mels, double 
     return w;
 }
 
-// Per-filter line coefficients: weight(k) = max(0, min(a_r k + b_r, a_f k + b_f)), the triangle of
-// librosa.filters.mel with the Slaney area normalisation folded in (evaluated in fp32 by the kernels; agrees with the
-// float32 matrix to ~1e-6 of the peak weight).
-inline std::vector<float> make_mel_coefficients(int sr, int n_fft, int n_mels, double fmin, double fmax) {
+// ---- moment form of the triangular filterbank ----------------------------------------------------------------------
+// Between two consecutive mel points every filter weight is a straight line in the bin index, so
+//     mel_m = sum_k P_k w_m(k) = ar_m S1_m + br_m S0_m + af_m S1_{m+1} + bf_m S0_{m+1}
+// with the per-segment moments S0_s = sum P_k, S1_s = sum (k - kb_s) P_k over the bins kb_s <= k < kb_{s+1} of segment
+// s (segment m carries the rising edge of filter m, segment m+1 its falling edge).  Each bin is touched once instead
+// of once per overlapping filter and no weight table is read.  The bins are cut into pieces of <= 33 bins, one per
+// thread, so the accumulation needs no cross-lane reduction.  The lines are those of librosa.filters.mel (Slaney area
+// normalisation folded in), evaluated in fp32 by the kernels: they agree with the float32 matrix to ~1e-6 of the peak.
+struct MelTabEntry {
+    int x, y, z, w;
+};
+constexpr int kMelSegments = 65;
+constexpr int kMelPieceLen = 33;      // bins per piece: consecutive lanes start on consecutive banks
+constexpr int kMelMaxPieces = 576;
+constexpr int kMelTabEntries = kMelMaxPieces / 2 + 80;      // int4 entries: 2 pieces each, then 65 segment ranges
+
+// One piece per thread: tab[i/2].{x,y} or .{z,w} = {first bin | length << 16, first bin of the segment}; a piece's
+// partial moments go to slot i.  tab[kMelMaxPieces/2 + s] = {first piece, number of pieces, 0, 0} of segment s.
+// coef[4 m .. +3] = {ar, br, af, bf} of filter m (br, bf already expressed in segment-local bin coordinates).
+inline bool make_mel_moment_tables(int sr, int n_fft, int n_mels, double fmin, double fmax,
+                                   std::vector<MelTabEntry>& tab, std::vector<float>& coef, int& n_pieces) {
+    if (n_mels + 1 != kMelSegments) return false;
+    const int n_bins = n_fft / 2 + 1;
     std::vector<double> mel_f(n_mels + 2);
     const double lo = hz_to_mel(fmin), hi = hz_to_mel(fmax);
     const double step = (hi - lo) / (n_mels + 1);
     for (int i = 0; i < n_mels + 2; ++i) mel_f[i] = mel_to_hz(i == n_mels + 1 ? hi : lo + step * i);
     const double val = 1.0 / (static_cast<double>(n_fft) * (1.0 / sr));
-    std::vector<float> c(static_cast<size_t>(n_mels) * 4);
-    for (int i = 0; i < n_mels; ++i) {
-        const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
-        const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
-        c[4 * i + 0] = static_cast<float>(val * enorm / fd0);
-        c[4 * i + 1] = static_cast<float>(-mel_f[i] * enorm / fd0);
-        c[4 * i + 2] = static_cast<float>(-val * enorm / fd1);
-        c[4 * i + 3] = static_cast<float>(mel_f[i + 2] * enorm / fd1);
+    std::vector<int> kb(n_mels + 2);
+    for (int i = 0; i < n_mels + 2; ++i) {
+        int k = static_cast<int>(std::ceil(mel_f[i] / val - 1e-9));
+        if (k < 0) k = 0;
+        if (k > n_bins) k = n_bins;
+        kb[i] = k;
     }
-    return c;
-}
-
-struct MelTabEntry {
-    int x, y, z, w;
-};
-constexpr int kMelRows = 16;          // work rows (one per worker warp of the fused kernel)
-constexpr int kMelSegsPerRow = 16;
-constexpr int kMelTabEntries = kMelRows * kMelSegsPerRow + 64;
-
-// Compact, load-balanced form of the filterbank for the kernels:
-//   weights : per filter the contiguous run of non-zero weights, extended down to a multiple of 4 bins and padded
-//             to a multiple of 4 entries (float4 loads);
-//   tab[row*16 + s] = {first bin, filter index, float4 count, partial-sum slot}  -- segments of work row `row`
-//             (a filter may be split over consecutive rows; count 0 terminates a row);
-//   tab[256 + m]    = {first slot, number of slots, 0, 0} of filter m (partials are summed in slot order).
-inline bool make_mel_segments(const std::vector<float>& dense, int n_bins, int n_mels, std::vector<MelTabEntry>& tab,
-                              std::vector<float>& weights, int& n_slots) {
+    coef.assign(static_cast<size_t>(n_mels) * 4, 0.f);
+    for (int m = 0; m < n_mels; ++m) {
+        const double fd0 = mel_f[m + 1] - mel_f[m], fd1 = mel_f[m + 2] - mel_f[m + 1];
+        const double enorm = 2.0 / (mel_f[m + 2] - mel_f[m]);
+        const double ar = val * enorm / fd0, br = -mel_f[m] * enorm / fd0;
+        const double af = -val * enorm / fd1, bf = mel_f[m + 2] * enorm / fd1;
+        coef[4 * m + 0] = static_cast<float>(ar);
+        coef[4 * m + 1] = static_cast<float>(ar * kb[m] + br);
+        coef[4 * m + 2] = static_cast<float>(af);
+        coef[4 * m + 3] = static_cast<float>(af * kb[m + 1] + bf);
+    }
     tab.assign(kMelTabEntries, MelTabEntry{0, 0, 0, 0});
-    weights.clear();
-    std::vector<int> first(n_mels), n4(n_mels), woff(n_mels);
-    long long total_cost = 0;
-    auto cost = [](int items) { return (items + 31) / 32 + 2; };
-    for (int m = 0; m < n_mels; ++m) {
-        int lo = -1, hi = -1;
-        for (int k = 0; k < n_bins; ++k)
-            if (dense[static_cast<size_t>(k) * n_mels + m] != 0.f) {
-                if (lo < 0) lo = k;
-                hi = k;
-            }
-        if (lo < 0) { lo = 0; hi = -1; }
-        lo &= ~3;
-        int cnt = hi - lo + 1;
-        if (cnt < 0) cnt = 0;
-        const int cnt_pad = (cnt + 3) & ~3;
-        first[m] = lo;
-        n4[m] = cnt_pad / 4;
-        woff[m] = static_cast<int>(weights.size());
-        for (int i = 0; i < cnt_pad; ++i) {
-            const int k = lo + i;
-            weights.push_back(k < n_bins ? dense[static_cast<size_t>(k) * n_mels + m] : 0.f);
+    int piece = 0;
+    for (int s = 0; s < kMelSegments; ++s) {
+        const int first_piece = piece;
+        for (int k = kb[s]; k < kb[s + 1]; k += kMelPieceLen) {
+            if (piece >= kMelMaxPieces) return false;
+            const int len = (kb[s + 1] - k < kMelPieceLen) ? kb[s + 1] - k : kMelPieceLen;
+            MelTabEntry& e = tab[piece / 2];
+            if (piece & 1) { e.z = k | (len << 16); e.w = kb[s]; }
+            else           { e.x = k | (len << 16); e.y = kb[s]; }
+            ++piece;
         }
-        total_cost += cost(n4[m]);
+        tab[kMelMaxPieces / 2 + s] = MelTabEntry{first_piece, piece - first_piece, 0, 0};
     }
-    const long long quota = (total_cost + kMelRows - 1) / kMelRows + 1;
-    int row = 0, seg = 0, slot = 0;
-    long long used = 0;
-    for (int m = 0; m < n_mels; ++m) {
-        int done = 0;
-        tab[kMelRows * kMelSegsPerRow + m] = MelTabEntry{slot, 0, 0, 0};
-        if (n4[m] == 0) continue;
-        while (done < n4[m]) {
-            if ((used >= quota || seg >= kMelSegsPerRow) && row + 1 < kMelRows) {
-                ++row;
-                seg = 0;
-                used = 0;
-            }
-            if (seg >= kMelSegsPerRow) return false;
-            long long room = (quota - used - 2) * 32;                 // float4 items that still fit this row
-            if (room < 32) room = 32;
-            int take = n4[m] - done;
-            if (take > room && row + 1 < kMelRows) take = static_cast<int>(room);
-            tab[row * kMelSegsPerRow + seg] = MelTabEntry{first[m] + 4 * done, m, take, slot};
-            tab[kMelRows * kMelSegsPerRow + m].y += 1;
-            used += cost(take);
-            done += take;
-            ++seg;
-            ++slot;
-        }
-    }
-    n_slots = slot;
-    return slot <= 128;
+    n_pieces = piece;
+    return true;
 }
 
 }  // namespace sedb_host

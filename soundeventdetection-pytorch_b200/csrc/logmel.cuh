@@ -53,10 +53,11 @@ constexpr int kOffAlt = kOffRing + kRingBytes;             // per-row alternatin
 constexpr int kOffX128 = kOffAlt + 16 * 128 * 4;           // X[128, n2]      128 floats
 constexpr int kOffV = kOffX128 + 512;                      // Y[n2,128]       128 floats
 constexpr int kOffCs = kOffV + 512;                        // exp(-2 pi i j/256) 256 float2
-constexpr int kMelTabEntries = 16 * 16 + 64;               // host_tables.h: make_mel_segments
+constexpr int kMelMaxPieces = 576;                         // host_tables.h: make_mel_moment_tables
+constexpr int kMelTabEntries = kMelMaxPieces / 2 + 80;
 constexpr int kOffMelTab = kOffCs + 2048;                  // segment table (320 x int4)
-constexpr int kOffMelPart = kOffMelTab + kMelTabEntries * 16;   // partial sums (128 floats)
-constexpr int kOffMelCoef = kOffMelPart + 512;             // 64 x float4 line coefficients
+constexpr int kOffMelPart = kOffMelTab + kMelTabEntries * 16;   // partial moments (2 x kMelMaxPieces floats)
+constexpr int kOffMelCoef = kOffMelPart + 2 * kMelMaxPieces * 4;   // 64 x float4 line coefficients
 constexpr int kOffNorm = kOffMelCoef + 1024;               // mean[64], std[64] (when given)
 constexpr int kOffRed = kOffNorm + 512;                    // absmax reduction scratch (16 floats) + scale
 constexpr int kOffBars = kOffRed + 128;                    // mbarriers
@@ -80,8 +81,8 @@ struct LogmelParams {
     const uint8_t* a1;        // stage-1 constants, 8 chunks x 16 KB, canonical K-major, split hi/lo
     const uint8_t* b2;        // stage-2 constants, 4 x 16 KB
     const float* hann;        // np.hanning(31680) centre-padded to 32768
-    const float* mel_w;       // 64 x {a_r, b_r, a_f, b_f}: weight(k) = max(0, min(a_r k + b_r, a_f k + b_f))
-    const int4* mel_tab;      // balanced segment table + per-filter slot ranges (host_tables.h)
+    const float* mel_w;       // 64 x {ar, br, af, bf}: line coefficients of the moment form (host_tables.h)
+    const int4* mel_tab;      // balanced piece table + per-segment slot ranges (host_tables.h)
     const float* norm;        // nullable: mean[64] then std[64]  (SpectogramDataset.transform, logMel mode)
     float* out;               // MODE 0: [B, T, 64] fp32 log-mel
     float2* spec;             // MODE 1: [B, T, 16385] complex64 STFT
@@ -136,48 +137,46 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
     lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// Banded mel dot products over a power spectrum in shared memory.  The 64 filters are cut into load-balanced
-// segments (16 work rows); every segment's partial sum goes to a fixed slot and the slots of a filter are added in
-// slot order, so the result does not depend on scheduling.  Called by `nwarps` warps, followed by a block-level
-// barrier and mel_finalize().
+// Mel filterbank over a power spectrum in shared memory, in moment form (host_tables.h): per segment between two mel
+// points S0 = sum P_k and S1 = sum (k - kb) P_k.  The bins are cut into pieces of <= 33 bins; thread `idx` accumulates
+// pieces idx, idx + nthreads, ... serially (two independent chains, no cross-lane reduction; consecutive lanes start on
+// consecutive banks) and writes the partial moments to the piece's own slot.  The slots of a segment are then added in
+// order by mel_finalize(), so the result does not depend on scheduling.  A block-level barrier goes in between.
 __device__ __forceinline__ void mel_partials(const float* __restrict__ p_s, const int4* __restrict__ tab_s,
-                                             const float* __restrict__ mel_w, float* __restrict__ part_s, int warp,
-                                             int lane, int nwarps) {
-    for (int row = warp; row < 16; row += nwarps) {
-#pragma unroll 1
-        for (int sg = 0; sg < 16; ++sg) {
-            const int4 e = tab_s[row * 16 + sg];
-            if (e.z == 0) break;
-            const float4 cf = reinterpret_cast<const float4*>(mel_w)[e.y];
-            const float4* p = reinterpret_cast<const float4*>(p_s + e.x);
-            float acc0 = 0.f, acc1 = 0.f;
-            for (int j = lane; j < e.z; j += 32) {
-                const float4 pv = p[j];
-                const float k = static_cast<float>(e.x + 4 * j);
-                const float r0 = fmaf(cf.x, k, cf.y), f0 = fmaf(cf.z, k, cf.w);
-                const float r1 = r0 + cf.x, f1 = f0 + cf.z;
-                const float r2 = r1 + cf.x, f2 = f1 + cf.z;
-                const float r3 = r2 + cf.x, f3 = f2 + cf.z;
-                acc0 = fmaf(pv.x, fmaxf(0.f, fminf(r0, f0)), acc0);
-                acc1 = fmaf(pv.y, fmaxf(0.f, fminf(r1, f1)), acc1);
-                acc0 = fmaf(pv.z, fmaxf(0.f, fminf(r2, f2)), acc0);
-                acc1 = fmaf(pv.w, fmaxf(0.f, fminf(r3, f3)), acc1);
-            }
-            float acc = acc0 + acc1;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) part_s[e.w] = acc;
+                                             float* __restrict__ part_s, int idx, int nthreads) {
+    const int2* pieces = reinterpret_cast<const int2*>(tab_s);
+    for (int i = idx; i < kMelMaxPieces; i += nthreads) {
+        const int2 e = pieces[i];
+        const int k0 = e.x & 0xffff, len = e.x >> 16;
+        const float* p = p_s + k0;
+        float s0 = 0.f, s1 = 0.f, kf = static_cast<float>(k0 - e.y);
+#pragma unroll 4
+        for (int j = 0; j < len; ++j) {
+            const float v = p[j];
+            s0 += v;
+            s1 = fmaf(kf, v, s1);
+            kf += 1.0f;
         }
+        part_s[i] = s0;
+        part_s[kMelMaxPieces + i] = s1;
     }
 }
-// threads 0..63: sum the partial slots of filter `tid`, convert to dB, normalise, store.
+// threads 0..63: combine the moments of segments tid and tid+1 into filter `tid`, convert to dB, normalise, store.
 __device__ __forceinline__ void mel_finalize(const float* __restrict__ part_s, const int4* __restrict__ tab_s,
-                                             const float* __restrict__ norm, float inv_scale2,
-                                             float* __restrict__ out_row, int tid) {
+                                             const float* __restrict__ coef_s, const float* __restrict__ norm,
+                                             float inv_scale2, float* __restrict__ out_row, int tid) {
     if (tid < kMel) {
-        const int4 f = tab_s[256 + tid];
-        float a = 0.f;
-        for (int i = 0; i < f.y; ++i) a += part_s[f.x + i];
+        float m0[2] = {0.f, 0.f}, m1[2] = {0.f, 0.f};
+#pragma unroll
+        for (int d = 0; d < 2; ++d) {
+            const int4 f = tab_s[kMelMaxPieces / 2 + tid + d];
+            for (int i = 0; i < f.y; ++i) {
+                m0[d] += part_s[f.x + i];
+                m1[d] += part_s[kMelMaxPieces + f.x + i];
+            }
+        }
+        const float4 cf = reinterpret_cast<const float4*>(coef_s)[tid];
+        const float a = fmaf(cf.x, m1[0], cf.y * m0[0]) + fmaf(cf.z, m1[1], cf.w * m0[1]);
         float db = 10.0f * log10f(fmaxf(1e-10f, a * inv_scale2));        // librosa.power_to_db(ref=1, amin=1e-10)
         if (norm != nullptr) db = (db - norm[tid]) / norm[kMel + tid];   // spectograms_dataset.py:105
         out_row[tid] = db;
@@ -603,12 +602,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 if (tid < 3) p_s[kBins + tid] = 0.f;                  // padding read by the vectorised mel bands
                 worker_sync();                                        // power spectrum complete
                 SEDB_PROF(8);
-                mel_partials(p_s, mel_tab_s, coef_s, part_s, warp, lane, kWorkerWarps);
+                mel_partials(p_s, mel_tab_s, part_s, tid, kWorkerThreads);
                 SEDB_PROF(9);
                 worker_sync();
                 SEDB_PROF(10);
                 float* out_row = prm.out + (static_cast<long long>(clip) * prm.n_frames + t) * kMel;
-                mel_finalize(part_s, mel_tab_s, prm.norm != nullptr ? norm_s : nullptr, inv_scale * inv_scale, out_row, tid);
+                mel_finalize(part_s, mel_tab_s, coef_s, prm.norm != nullptr ? norm_s : nullptr, inv_scale * inv_scale,
+                             out_row, tid);
                 SEDB_PROF(11);
             }
             worker_sync();                                            // ring (aliased by p_s) may be refilled
@@ -636,7 +636,7 @@ __global__ void __launch_bounds__(256) power_mel_db_kernel(const float2* __restr
     float* p_s = reinterpret_cast<float*>(smem);
     int4* mel_tab_s = reinterpret_cast<int4*>(smem + ((kBins * 4 + 16 + 15) / 16) * 16);
     float* part_s = reinterpret_cast<float*>(mel_tab_s + kMelTabEntries);
-    float* coef_s = part_s + 128;
+    float* coef_s = part_s + 2 * kMelMaxPieces;
     const int tid = threadIdx.x;
     for (int i = tid; i < kMelTabEntries; i += 256) mel_tab_s[i] = mel_tab[i];
     for (int i = tid; i < 4 * kMel; i += 256) coef_s[i] = mel_w[i];
@@ -648,9 +648,9 @@ __global__ void __launch_bounds__(256) power_mel_db_kernel(const float2* __restr
             p_s[k] = v.x * v.x + v.y * v.y;
         }
         __syncthreads();
-        mel_partials(p_s, mel_tab_s, coef_s, part_s, tid >> 5, tid & 31, 8);
+        mel_partials(p_s, mel_tab_s, part_s, tid, 256);
         __syncthreads();
-        mel_finalize(part_s, mel_tab_s, norm, 1.0f, out + row * kMel, tid);
+        mel_finalize(part_s, mel_tab_s, coef_s, norm, 1.0f, out + row * kMel, tid);
         __syncthreads();
     }
 }

@@ -107,14 +107,12 @@ int sedb_create(sedb_ctx_t** out_ctx) {
     c->num_sms = prop.multiProcessorCount;
     std::vector<uint8_t> a1 = sedb_host::make_stage1_constants(kFp16);
     std::vector<uint8_t> b2 = sedb_host::make_stage2_constants(kFp16);
-    std::vector<float> dense = sedb_host::make_mel_matrix(SEDB_SAMPLE_RATE, SEDB_NFFT, SEDB_MEL_BINS, SEDB_MEL_FMIN,
-                                                          SEDB_MEL_FMAX);
     std::vector<sedb_host::MelTabEntry> tab;
     std::vector<float> wts;
     int mel_slots = 0;
-    if (!sedb_host::make_mel_segments(dense, SEDB_NUM_BINS, SEDB_MEL_BINS, tab, wts, mel_slots))
+    if (!sedb_host::make_mel_moment_tables(SEDB_SAMPLE_RATE, SEDB_NFFT, SEDB_MEL_BINS, SEDB_MEL_FMIN, SEDB_MEL_FMAX, tab,
+                                           wts, mel_slots))
         return fail("sedb_create: mel work table does not fit");
-    wts = sedb_host::make_mel_coefficients(SEDB_SAMPLE_RATE, SEDB_NFFT, SEDB_MEL_BINS, SEDB_MEL_FMIN, SEDB_MEL_FMAX);
     CUDA_TRY(cudaMalloc(&c->a1, a1.size()));
     CUDA_TRY(cudaMalloc(&c->b2, b2.size()));
     std::vector<float> hann = sedb_host::make_hann_padded(SEDB_FRAME_SIZE, SEDB_NFFT);
@@ -131,7 +129,7 @@ int sedb_create(sedb_ctx_t** out_ctx) {
     CUDA_TRY(cudaFuncSetAttribute(sedb::logmel_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   sedb::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(sedb::power_mel_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  72 * 1024));
+                                  80 * 1024));
     if (int rc = sedb_cnn_kernels_init()) return rc;
     *out_ctx = c;
     return 0;
@@ -215,7 +213,7 @@ int sedb_power_mel_db_f32(sedb_ctx_t* c, const float* spec_dev, long long rows, 
     if (rows == 0) return 0;
     if (!spec_dev || !out_dev) return fail("null buffer");
     const int grid = static_cast<int>(rows < 4LL * c->num_sms ? rows : 4LL * c->num_sms);
-    sedb::power_mel_db_kernel<<<grid, 256, 72 * 1024, static_cast<cudaStream_t>(stream)>>>(
+    sedb::power_mel_db_kernel<<<grid, 256, 80 * 1024, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float2*>(spec_dev), rows, c->mel_w, c->mel_tab, norm_dev, out_dev);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
