@@ -125,8 +125,13 @@ int sedb_sed_host_f32(sedb_ctx_t* ctx, sedb_cnn_t* cnn, const float* wave_host, 
  * stride; neg_b: set the B-negate bit. */
 int sedb_debug_umma_probe(const float* a_dev, const float* b_dev, float* d_dev, int N, int K, int a_major,
                           int b_major, int pad, int neg_b, int swap_lbo_sbo, void* stream);
+/* tcgen05.mma issue-to-completion throughput probe: `grid` CTAs each issue `reps` MMAs of 128 x N x 16 over n_acc
+ * accumulator tiles; cycles_host receives block 0's total cycles. */
+int sedb_debug_umma_rate(int N, int b_major, int n_acc, int reps, int lbo_a, int lbo_b, int grid,
+                         unsigned long long* cycles_host);
 /* Per-phase cycle counters of logmel_fused_kernel (thread 0 of every CTA, summed): enable != 0 switches the
- * instrumentation on; out_host16 (nullable) receives and clears the 16 counters; enable == 0 switches it off. */
+ * instrumentation on; out_host16 (nullable) receives and clears 128 counters (16 for the log-mel kernel, then 16 per
+ * conv layer of the next CNN forward); enable == 0 switches it off. */
 int sedb_debug_phase_profile(int enable, unsigned long long* out_host16);
 /* Number of kernel launches issued through this library since load (bench.py's gpu_launches). */
 long long sedb_launch_count(void);

@@ -52,6 +52,7 @@ _SIGNATURES = {
                                          c_float_p]),
     "sedb_debug_umma_probe": (ctypes.c_int, [c_float_p, c_float_p, c_float_p] + [ctypes.c_int] * 7
                               + [ctypes.c_void_p]),
+    "sedb_debug_umma_rate": (ctypes.c_int, [ctypes.c_int] * 7 + [ctypes.c_void_p]),
     "sedb_debug_phase_profile": (ctypes.c_int, [ctypes.c_int, ctypes.c_void_p]),
     "sedb_launch_count": (c_ll, []),
 }

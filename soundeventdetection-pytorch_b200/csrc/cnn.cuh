@@ -19,9 +19,18 @@
 
 namespace sedb {
 
+#define CONV_PROF(i)                                                                   \
+    do {                                                                               \
+        if (p.prof != nullptr && (threadIdx.x & 31) == 0) {                             \
+            const long long now__ = clock64();                                         \
+            atomicAdd(p.prof + (i), static_cast<unsigned long long>(now__ - tprev));   \
+            tprev = now__;                                                             \
+        }                                                                              \
+    } while (0)
+
 constexpr int kConvThreads = 320;          // 8 epilogue warps + MMA warp + copy warp
-constexpr int kConvWSlots = 6;
-constexpr int kConvWSlotBytes = 128 * 64;  // one (tap, 16-channel) weight block: hi|lo x [cout_tile][16]
+constexpr int kConvMaxWSlots = 6;
+constexpr int kConvMaxWSlotBytes = 16384;  // weight ring slot: `kpb` consecutive (tap, 16-channel) blocks of hi|lo x [cout_tile][16]
 constexpr int kConvLead = 8;
 
 struct ConvParams {
@@ -42,6 +51,12 @@ struct ConvParams {
     int ntaps;
     int tapoff[9];           // tap offsets in pixels relative to the patch start
     int patch_bytes;         // 2 * (cin_chunk/8) * P * 16
+    int n_wslots;            // weight ring slots (<= kConvMaxWSlots)
+    int kpb;                 // 16-channel K-steps per weight ring slot (divides cin_chunk/16)
+    int wslot_bytes;         // kpb * cout_tile * 64
+    int stage_bytes;         // pooling stage (0 without pooling)
+    unsigned long long* prof; // nullable diagnostics: [0] epilogue wait, [1] epilogue work, [2] mma wait patch,
+                              // [3] mma wait weights, [4] mma wait tmem, [5] copy wait patch_free, [6] items
 };
 
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
@@ -62,35 +77,39 @@ __device__ __forceinline__ void store_split8(uint8_t* hi_ptr, uint8_t* lo_ptr, c
     *reinterpret_cast<uint4*>(lo_ptr) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// shared memory: [patch | weight ring | scale/shift | barriers | tmem ptr]; the pooling stage aliases the patch.
+// shared memory: [patch | weight ring | pooling stage | scale/shift | barriers | tmem ptr].  The accumulators are double
+// buffered in TMEM (columns 0..255 / 256..511 for even / odd work items) so that the patch load and the MMAs of item
+// t+1 overlap the epilogue of item t.
 __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* patch = smem;
     uint8_t* wring = smem + ((p.patch_bytes + 127) / 128) * 128;
-    float* sc_s = reinterpret_cast<float*>(wring + kConvWSlots * kConvWSlotBytes);
+    float* stage = reinterpret_cast<float*>(wring + p.n_wslots * p.wslot_bytes);
+    float* sc_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(stage) + p.stage_bytes);
     float* sh_s = sc_s + p.cout;
     uint64_t* bars = reinterpret_cast<uint64_t*>(
         (reinterpret_cast<uintptr_t>(sh_s + p.cout) + 15) & ~static_cast<uintptr_t>(15));
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 24);
-    float* stage = reinterpret_cast<float*>(patch);
 
     uint64_t* wfull = bars + 0;        // [6]
     uint64_t* wempty = bars + 6;       // [6]
     uint64_t* patch_full = bars + 12;
     uint64_t* patch_free = bars + 13;
-    uint64_t* acc_full = bars + 14;
-    uint64_t* epi_done = bars + 15;
+    uint64_t* acc_full = bars + 14;    // [2]
+    uint64_t* epi_done = bars + 16;    // [2]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
-        for (int s = 0; s < kConvWSlots; ++s) {
+        for (int s = 0; s < kConvMaxWSlots; ++s) {
             mbar_init(&wfull[s], 1);
             mbar_init(&wempty[s], 1);
         }
         mbar_init(patch_full, 1);
         mbar_init(patch_free, 1);
-        mbar_init(acc_full, 1);
-        mbar_init(epi_done, 8);
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&epi_done[s], 8);
+        }
         mbar_fence_init();
     }
     if (warp == 8) tmem_alloc<512>(tmem_ptr_s);
@@ -123,76 +142,114 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
     auto band_v0 = [&](int band) { return p.mode == 0 ? (p.R * band + 1) * p.Wp : 1 + band * 128 * p.n_tiles; };
 
     if (warp == 9) {
-        // ================================================================ bulk-copy producer
-        if (lane == 0) {
+        // ================================================================ bulk-copy producer (converged warp, one
+        // elected lane issues; see the note in the MMA issuer)
+        {
             int gw = 0;
+            long long tprev = clock64();
             for (int it = 0; it < n_items; ++it) {
                 int img, band, ntile;
                 decode(it, img, band, ntile);
                 const int v0 = band_v0(band);
                 for (int kc = 0; kc < p.n_kchunks; ++kc) {
                     const int gk = it * p.n_kchunks + kc;
+                    tprev = clock64();
                     if (gk > 0) mbar_wait(patch_free, (gk - 1) & 1);
-                    if (kc == 0 && it > 0) mbar_wait(epi_done, (it - 1) & 1);
-                    mbar_arrive_expect_tx(patch_full, p.patch_bytes);
-                    for (int arr = 0; arr < 2; ++arr)
-                        for (int kgl = 0; kgl < kg_chunk; ++kgl) {
-                            const long long plane = (static_cast<long long>(img) * 2 + arr) * (p.cin / 8) + kc * kg_chunk + kgl;
-                            const uint8_t* src = p.in + (plane * p.S_in + kConvLead + v0 - p.halo) * 16;
-                            bulk_g2s(patch + (arr * kg_chunk + kgl) * p.P * 16, src, p.P * 16, patch_full);
-                        }
+                    CONV_PROF(5);
+                    if (elect_one()) {
+                        mbar_arrive_expect_tx(patch_full, p.patch_bytes);
+                        for (int arr = 0; arr < 2; ++arr)
+                            for (int kgl = 0; kgl < kg_chunk; ++kgl) {
+                                const long long plane =
+                                    (static_cast<long long>(img) * 2 + arr) * (p.cin / 8) + kc * kg_chunk + kgl;
+                                const uint8_t* src = p.in + (plane * p.S_in + kConvLead + v0 - p.halo) * 16;
+                                bulk_g2s(patch + (arr * kg_chunk + kgl) * p.P * 16, src, p.P * 16, patch_full);
+                            }
+                    }
+                    __syncwarp();
                     const uint8_t* wsrc = p.wpack + static_cast<long long>(ntile * p.n_kchunks + kc) * blocks_per_kc * wblock_bytes;
-                    for (int b = 0; b < blocks_per_kc; ++b, ++gw) {
-                        const int s = gw % kConvWSlots, u = gw / kConvWSlots;
+                    const int group_bytes = p.kpb * wblock_bytes;
+                    for (int b = 0; b < blocks_per_kc; b += p.kpb, ++gw) {
+                        const int s = gw % p.n_wslots, u = gw / p.n_wslots;
                         mbar_wait(&wempty[s], (u & 1) ^ 1);
-                        mbar_arrive_expect_tx(&wfull[s], wblock_bytes);
-                        bulk_g2s(wring + s * kConvWSlotBytes, wsrc + static_cast<long long>(b) * wblock_bytes, wblock_bytes, &wfull[s]);
+                        if (elect_one()) {
+                            mbar_arrive_expect_tx(&wfull[s], group_bytes);
+                            bulk_g2s(wring + s * p.wslot_bytes, wsrc + static_cast<long long>(b) * wblock_bytes,
+                                     group_bytes, &wfull[s]);
+                        }
+                        __syncwarp();
                     }
                 }
             }
         }
     } else if (warp == 8) {
-        // ================================================================ MMA issuer
-        if (lane == 0) {
+        // ================================================================ MMA issuer: the warp stays converged and one
+        // elected lane issues, so that all operands are warp-uniform (TMEM base of the 512-column allocation is 0)
+        if (tmem != 0) __trap();
+        {
             const uint32_t idesc = make_idesc(kFmtBF16, kMajorK, kMajorK, 128, p.cout_tile);
             const uint32_t patch_a = smem_u32(patch);
             const uint32_t wring_a = smem_u32(wring);
             const uint32_t a_lbo = p.P * 16;
             const uint32_t b_lbo = p.cout_tile * 16;
-            const uint32_t lo_arr = kg_chunk * p.P * 16;       // offset of the lo half of the patch
+            const uint64_t a_base = make_smem_desc(patch_a, a_lbo, 128);
+            const uint64_t b_base = make_smem_desc(wring_a, b_lbo, 128);
+            const uint32_t a_lo_delta = kg_chunk * p.P;            // lo half of the patch, in 16-byte units
+            const uint32_t b_lo_delta = p.cout_tile * 2;           // lo half of a weight block
             int gw = 0;
+            long long tprev = clock64();
             for (int it = 0; it < n_items; ++it) {
-                if (it > 0) {
-                    mbar_wait(epi_done, (it - 1) & 1);
+                const uint32_t acc_base = 256 * (it & 1);
+                tprev = clock64();
+                if (it >= 2) {                                  // this accumulator buffer was last drained by item it-2
+                    mbar_wait(&epi_done[it & 1], ((it - 2) >> 1) & 1);
                     tc_fence_after();
                 }
+                CONV_PROF(4);
                 for (int kc = 0; kc < p.n_kchunks; ++kc) {
                     const int gk = it * p.n_kchunks + kc;
                     mbar_wait(patch_full, gk & 1);
                     tc_fence_after();
-                    for (int b = 0; b < blocks_per_kc; ++b, ++gw) {
-                        const int tap = b / ks_chunk, ks = b % ks_chunk;
-                        const int s = gw % kConvWSlots, u = gw / kConvWSlots;
-                        mbar_wait(&wfull[s], u & 1);
-                        tc_fence_after();
-                        const uint32_t wb = wring_a + s * kConvWSlotBytes;
-                        const uint64_t bH = make_smem_desc(wb, b_lbo, 128);
-                        const uint64_t bL = make_smem_desc(wb + p.cout_tile * 32, b_lbo, 128);
-                        const uint32_t acc = (kc > 0 || b > 0) ? 1u : 0u;
-                        for (int m = 0; m < p.n_tiles; ++m) {
-                            const uint32_t a_addr = patch_a + (2 * ks * p.P + 128 * m + p.tapoff[tap]) * 16;
-                            const uint64_t aH = make_smem_desc(a_addr, a_lbo, 128);
-                            const uint64_t aL = make_smem_desc(a_addr + lo_arr, a_lbo, 128);
-                            const uint32_t d = tmem + m * p.cout_tile;
-                            umma_f16(d, aH, bH, idesc, acc);
-                            umma_f16(d, aL, bH, idesc, 1u);
-                            umma_f16(d, aH, bL, idesc, 1u);
+                    CONV_PROF(2);
+                    // Descriptors differ only in their start-address field (16-byte units, low 14 bits), so every
+                    // operand is the base descriptor plus an offset: the single issuing thread stays a few
+                    // instructions per MMA.
+                    for (int tap = 0; tap < p.ntaps; ++tap) {
+                        const uint32_t tap_off = p.tapoff[tap];
+                        for (int ks0 = 0; ks0 < ks_chunk; ks0 += p.kpb, ++gw) {
+                            const int s = gw % p.n_wslots, u = gw / p.n_wslots;
+                            mbar_wait(&wfull[s], u & 1);
+                            tc_fence_after();
+                            if (elect_one()) {
+                                uint64_t bH = b_base + static_cast<uint32_t>(s * (p.wslot_bytes >> 4));
+                                for (int j = 0; j < p.kpb; ++j) {
+                                    const uint64_t bL = bH + b_lo_delta;
+                                    const uint32_t acc = (kc > 0 || tap > 0 || ks0 + j > 0) ? 1u : 0u;
+                                    uint64_t aH = a_base + (2 * (ks0 + j) * p.P + tap_off);
+                                    uint32_t d = acc_base;
+#pragma unroll 1
+                                    for (int m = 0; m < p.n_tiles; ++m) {
+                                        const uint64_t aL = aH + a_lo_delta;
+                                        umma_f16(d, aH, bH, idesc, acc);
+                                        umma_f16(d, aL, bH, idesc, 1u);
+                                        umma_f16(d, aH, bL, idesc, 1u);
+                                        aH += 128;
+                                        d += p.cout_tile;
+                                    }
+                                    bH += 2 * b_lo_delta;            // next 16-channel block of the group
+                                }
+                                umma_commit(&wempty[s]);
+                            }
+                            __syncwarp();
                         }
-                        umma_commit(&wempty[s]);
                     }
-                    umma_commit(patch_free);
+                    if (elect_one()) {
+                        umma_commit(patch_free);
+                        if (kc + 1 == p.n_kchunks) umma_commit(&acc_full[it & 1]);
+                    }
+                    __syncwarp();
+                    CONV_PROF(3);
                 }
-                umma_commit(acc_full);
             }
         }
     } else {
@@ -200,6 +257,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
         const int q = warp & 3, grp = warp >> 2;
         const uint32_t tlane = tmem + (static_cast<uint32_t>(q * 32) << 16);
         const int etid = tid;                                     // 0..255
+        long long tprev = clock64();
         for (int it = 0; it < n_items; ++it) {
             int img, band, ntile;
             decode(it, img, band, ntile);
@@ -213,8 +271,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
             } else {
                 npix = min(128 * p.n_tiles, p.W - band * 128 * p.n_tiles);
             }
-            mbar_wait(acc_full, it & 1);
+            mbar_wait(&acc_full[it & 1], (it >> 1) & 1);
             tc_fence_after();
+            if (tid == 0) { CONV_PROF(0); }
+            const uint32_t tacc = tlane + 256 * (it & 1);
             const long long out_img = static_cast<long long>(img) * 2 * (p.cout / 8);
             if (p.pool == 1) {
                 for (int m = grp; m < p.n_tiles; m += 2) {
@@ -227,7 +287,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                     const long long vout = kConvLead + v0 + pp;
                     for (int c0 = 0; c0 < p.cout_tile; c0 += 16) {
                         float acc[16];
-                        tmem_ld16(tlane + m * p.cout_tile + c0, acc);
+                        tmem_ld16(tacc + m * p.cout_tile + c0, acc);
                         tmem_ld_wait();
                         if (valid) {
 #pragma unroll
@@ -249,7 +309,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                     for (int m = grp; m < p.n_tiles; m += 2) {
                         const int pp = 128 * m + 32 * q + lane;
                         float acc[16];
-                        tmem_ld16(tlane + m * p.cout_tile + c0, acc);
+                        tmem_ld16(tacc + m * p.cout_tile + c0, acc);
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
@@ -301,7 +361,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(epi_done);
+            if (lane == 0) mbar_arrive(&epi_done[it & 1]);
+            if (tid == 0) { CONV_PROF(1); if (p.prof) atomicAdd(p.prof + 6, 1ull); }
         }
     }
     tc_fence_before();

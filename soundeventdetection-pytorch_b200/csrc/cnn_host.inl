@@ -18,6 +18,8 @@ struct UmmaLayer {          // a conv layer executed by conv_umma_kernel
 };
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
+bool conv_fit_smem(sedb::ConvParams& p);
+int plan_umma_layer_tiles(const UmmaLayer& L, int H, int W, int max_tiles, sedb::ConvParams& p);
 
 // Fills the launch parameters of one tensor-core conv layer for an input of H x W (2-D) or length W (1-D) and
 // returns the plane size S the *input* buffer must have.
@@ -35,7 +37,12 @@ int plan_umma_layer(const UmmaLayer& L, int H, int W, sedb::ConvParams& p) {
     p.n_ntiles = L.cout / L.cout_tile;
     p.pool = L.pool;
     p.ntaps = L.ntaps;
-    const int max_tiles = (L.cin_chunk <= 64) ? 4 : 2;
+    int max_tiles = (L.cin_chunk <= 64) ? 4 : 2;
+    if (max_tiles * L.cout_tile > 256) max_tiles = 256 / L.cout_tile;   // accumulators are double buffered in TMEM
+    return plan_umma_layer_tiles(L, H, W, max_tiles, p);
+}
+
+int plan_umma_layer_tiles(const UmmaLayer& L, int H, int W, int max_tiles, sedb::ConvParams& p) {
     if (L.mode == 0) {
         p.halo = p.Wp + 1;
         int R = (128 * max_tiles) / p.Wp;
@@ -64,16 +71,42 @@ int plan_umma_layer(const UmmaLayer& L, int H, int W, sedb::ConvParams& p) {
     }
     p.P = 128 * p.n_tiles + 2 * p.halo;
     p.patch_bytes = 2 * (L.cin_chunk / 8) * p.P * 16;
+    if (!conv_fit_smem(p)) {
+        if (max_tiles <= 1) return -1;
+        sedb::ConvParams q = p;                       // keep the layer description, retry with a smaller band
+        q.n_tiles = q.n_bands = q.R = q.P = 0;
+        p = q;
+        return plan_umma_layer_tiles(L, H, W, max_tiles - 1, p);
+    }
     const int v0_last = (L.mode == 0) ? (p.R * (p.n_bands - 1) + 1) * p.Wp : 1 + (p.n_bands - 1) * 128 * p.n_tiles;
     return round_up(sedb::kConvLead + v0_last - p.halo + p.P, 8);
 }
 
 size_t conv_smem_bytes(const sedb::ConvParams& p) {
-    size_t patch = static_cast<size_t>(p.patch_bytes);
-    const size_t stage = static_cast<size_t>(128) * p.n_tiles * 17 * 4;
-    if (p.pool != 1 && patch < stage) patch = stage;
-    patch = (patch + 127) / 128 * 128;
-    return patch + sedb::kConvWSlots * sedb::kConvWSlotBytes + static_cast<size_t>(2) * p.cout * 4 + 16 + 24 * 8 + 16 + 128;
+    const size_t patch = (static_cast<size_t>(p.patch_bytes) + 127) / 128 * 128;
+    return patch + static_cast<size_t>(p.n_wslots) * p.wslot_bytes + p.stage_bytes +
+           static_cast<size_t>(2) * p.cout * 4 + 16 + 24 * 8 + 16 + 128;
+}
+
+// Weight-ring geometry and pooling stage next to the patch: prefer several K-steps per slot (fewer barrier round
+// trips for the MMA issuer), then as many slots as fit.
+bool conv_fit_smem(sedb::ConvParams& p) {
+    p.stage_bytes = (p.pool != 1) ? 128 * p.n_tiles * 17 * 4 : 0;
+    const int ks_chunk = p.cin_chunk / 16;
+    const int wblock = p.cout_tile * 64;
+    for (int kpb = ks_chunk; kpb >= 1; --kpb) {
+        if (ks_chunk % kpb || kpb * wblock > sedb::kConvMaxWSlotBytes) continue;
+        p.kpb = kpb;
+        p.wslot_bytes = kpb * wblock;
+        for (int slots = sedb::kConvMaxWSlots; slots >= 3; --slots) {
+            p.n_wslots = slots;
+            if (conv_smem_bytes(p) <= 227 * 1024) return true;
+        }
+    }
+    p.kpb = 1;
+    p.wslot_bytes = wblock;
+    p.n_wslots = 2;
+    return conv_smem_bytes(p) <= 227 * 1024;
 }
 
 int final_plane_S(int mode, int H, int W) {
@@ -108,6 +141,7 @@ int launch_umma_layer(const sedb_ctx* c, const UmmaLayer& L, sedb::ConvParams p,
     p.n_img = n_img;
     p.S_in = S_in;
     p.S_out = S_out;
+    p.prof = g_prof ? g_prof + 16 * (1 + (g_conv_layer++ % 7)) : nullptr;
     const long long items = static_cast<long long>(n_img) * p.n_bands * p.n_ntiles;
     if (items <= 0) return 0;
     const int grid = static_cast<int>(items < c->num_sms ? items : c->num_sms);

@@ -45,6 +45,7 @@ constexpr int kSlotBytes = kA1ChunkBytes + 4 * kB1ArrBytes; // 34816: stage 1 (A
 constexpr int kNumSlots = 4;
 constexpr int kRingBytes = kSlotBytes * kNumSlots;         // 139264 (the power spectrum aliases the ring)
 constexpr int kA2ArrBytes = 128 * 16 * 2;                  // 4 KB
+static_assert((kNumSlots & (kNumSlots - 1)) == 0, "slot index uses a mask");
 static_assert(8 * kA2ArrBytes <= kSlotBytes, "stage-2 operands must fit a slot");
 
 constexpr int kOffB2 = 0;
@@ -256,96 +257,106 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
 
     // ======================================================================== bulk-copy producer warp
     if (warp == kCopyWarp) {
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_arrive_expect_tx(b2_full, kB2Bytes);
             for (int a = 0; a < 4; ++a)
                 bulk_g2s(b2_s + a * kB2ArrBytes, prm.b2 + a * kB2ArrBytes, kB2ArrBytes, b2_full);
-            for (int it = 0; it < n_iter; ++it) {
-                if (it > 0) mbar_wait(ring_free, (it - 1) & 1);
-                for (int c = 0; c < 8; ++c) {
-                    const int g = it * 8 + c;
-                    const int s = g % kNumSlots;
-                    const int u = g / kNumSlots;
-                    mbar_wait(&empty1[s], (u & 1) ^ 1);
+        }
+        __syncwarp();
+        for (int it = 0; it < n_iter; ++it) {
+            if (it > 0) mbar_wait(ring_free, (it - 1) & 1);
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+                const int g = it * 8 + c;
+                const int s = g & (kNumSlots - 1);
+                const int u = g / kNumSlots;
+                mbar_wait(&empty1[s], (u & 1) ^ 1);
+                if (elect_one()) {
                     mbar_arrive_expect_tx(&full1[s], kA1ChunkBytes);
                     bulk_g2s(ring + s * kSlotBytes, prm.a1 + c * kA1ChunkBytes, kA1ChunkBytes, &full1[s]);
                 }
-                // pull the next frame's samples towards L2 while this one is being processed
-                if (it + 1 < n_iter) {
-                    const long long f = blockIdx.x + static_cast<long long>(it + 1) * gridDim.x;
-                    const int clip = static_cast<int>(f / prm.n_frames);
-                    const int t = static_cast<int>(f - static_cast<long long>(clip) * prm.n_frames);
-                    const long long j0 = static_cast<long long>(t) * kHop + kLpad - kPadRefl;
-                    const float* src = prm.wave + static_cast<long long>(clip) * prm.wave_stride + j0;
-                    if (j0 >= 0 && j0 + kWin <= prm.n_samples && (reinterpret_cast<uintptr_t>(src) & 15) == 0)
+                __syncwarp();
+            }
+            // pull the next frame's samples towards L2 while this one is being processed
+            if (it + 1 < n_iter) {
+                const long long f = blockIdx.x + static_cast<long long>(it + 1) * gridDim.x;
+                const int clip = static_cast<int>(f / prm.n_frames);
+                const int t = static_cast<int>(f - static_cast<long long>(clip) * prm.n_frames);
+                const long long j0 = static_cast<long long>(t) * kHop + kLpad - kPadRefl;
+                const float* src = prm.wave + static_cast<long long>(clip) * prm.wave_stride + j0;
+                if (j0 >= 0 && j0 + kWin <= prm.n_samples && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+                    if (elect_one())
                         asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(kWin * 4) : "memory");
+                    __syncwarp();
                 }
             }
         }
     }
     // ======================================================================== MMA issuer warp
     else if (warp == kMmaWarp) {
-        if (lane == 0) {
-            constexpr uint32_t idesc1 = make_idesc(kSplitFmt, kMajorK, kMajorMN, 128, 128);
-            constexpr uint32_t idesc2 = make_idesc(kSplitFmt, kMajorK, kMajorK, 128, 128);
-            const uint32_t ring_a = smem_u32(ring);
-            const uint32_t b2_a = smem_u32(b2_s);
-            mbar_wait(b2_full, 0);
-            for (int it = 0; it < n_iter; ++it) {
-                // ---------------- stage 1: 8 K-chunks of 16 folded rows (m)
-                for (int c = 0; c < 8; ++c) {
-                    const int g = it * 8 + c;
-                    const int s = g % kNumSlots;
-                    const int u = g / kNumSlots;
-                    mbar_wait(&full1[s], u & 1);
-                    tc_fence_after();
-                    const uint32_t slot = ring_a + s * kSlotBytes;
-                    const uint64_t cH = make_smem_desc(slot + 0 * kA1ArrBytes, 2048, 128);
-                    const uint64_t cL = make_smem_desc(slot + 1 * kA1ArrBytes, 2048, 128);
-                    const uint64_t sH = make_smem_desc(slot + 2 * kA1ArrBytes, 2048, 128);
-                    const uint64_t sL = make_smem_desc(slot + 3 * kA1ArrBytes, 2048, 128);
-                    const uint32_t bb = slot + kA1ChunkBytes;
-                    const uint64_t uH = make_smem_desc(bb + 0 * kB1ArrBytes, kB1Lbo, kB1Sbo);
-                    const uint64_t uL = make_smem_desc(bb + 1 * kB1ArrBytes, kB1Lbo, kB1Sbo);
-                    const uint64_t vH = make_smem_desc(bb + 2 * kB1ArrBytes, kB1Lbo, kB1Sbo);
-                    const uint64_t vL = make_smem_desc(bb + 3 * kB1ArrBytes, kB1Lbo, kB1Sbo);
+        // The whole warp stays converged and one elected lane issues: every operand is then warp-uniform (the
+        // 512-column allocation starts at TMEM address 0) and each MMA costs a handful of uniform-datapath
+        // instructions.  A lane-divergent `if (lane == 0)` region makes ptxas wrap every tcgen05.mma in a vote loop.
+        if (tmem != 0) __trap();
+        constexpr uint32_t idesc1 = make_idesc(kSplitFmt, kMajorK, kMajorMN, 128, 128);
+        constexpr uint32_t idesc2 = make_idesc(kSplitFmt, kMajorK, kMajorK, 128, 128);
+        const uint32_t ring_a = smem_u32(ring);
+        const uint32_t b2_a = smem_u32(b2_s);
+        // descriptors for slot 0 / K-chunk 0; other slots and chunks add to the start-address field (16-byte units)
+        const uint64_t dA1 = make_smem_desc(ring_a, 2048, 128);                         // cH; cL, sH, sL follow
+        const uint64_t dB1 = make_smem_desc(ring_a + kA1ChunkBytes, kB1Lbo, kB1Sbo);     // uH; uL, vH, vL follow
+        const uint64_t dA2 = make_smem_desc(ring_a, 2048, 128);                         // stage-2 operand arrays
+        const uint64_t dB2 = make_smem_desc(b2_a, 2048, 128);                           // reH; reL, imH, imL follow
+        constexpr uint32_t kA1Step = kA1ArrBytes >> 4, kB1Step = kB1ArrBytes >> 4, kA2Step = kA2ArrBytes >> 4;
+        constexpr uint32_t kB2Step = kB2ArrBytes >> 4, kSlotStep = kSlotBytes >> 4;
+        mbar_wait(b2_full, 0);
+        for (int it = 0; it < n_iter; ++it) {
+            // ---------------- stage 1: 8 K-chunks of 16 folded rows (m)
+#pragma unroll 1
+            for (int c = 0; c < 8; ++c) {
+                const int g = it * 8 + c;
+                const int s = g & (kNumSlots - 1);
+                const int u = g / kNumSlots;
+                mbar_wait(&full1[s], u & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t a = dA1 + s * kSlotStep, bb = dB1 + s * kSlotStep;
                     const uint32_t acc = (c > 0) ? 1u : 0u;
-                    umma_f16(tmem + 0, cH, uH, idesc1, acc);
-                    umma_f16(tmem + 0, cL, uH, idesc1, 1u);
-                    umma_f16(tmem + 0, cH, uL, idesc1, 1u);
-                    umma_f16(tmem + 128, sH, vH, idesc1, acc);
-                    umma_f16(tmem + 128, sL, vH, idesc1, 1u);
-                    umma_f16(tmem + 128, sH, vL, idesc1, 1u);
+                    umma_f16(0, a, bb, idesc1, acc);                                   // cH uH
+                    umma_f16(0, a + kA1Step, bb, idesc1, 1u);                          // cL uH
+                    umma_f16(0, a, bb + kB1Step, idesc1, 1u);                          // cH uL
+                    umma_f16(128, a + 2 * kA1Step, bb + 2 * kB1Step, idesc1, acc);     // sH vH
+                    umma_f16(128, a + 3 * kA1Step, bb + 2 * kB1Step, idesc1, 1u);      // sL vH
+                    umma_f16(128, a + 2 * kA1Step, bb + 3 * kB1Step, idesc1, 1u);      // sH vL
                     umma_commit(&empty1[s]);
+                    if (c == 7) umma_commit(d1_full);
                 }
-                umma_commit(d1_full);
-                // ---------------- stage 2: 4 K-chunks of 16 columns (n), even and odd outputs
-                for (int j = 0; j < 4; ++j) {
-                    mbar_wait(&full2[j], it & 1);
-                    tc_fence_after();
-                    const uint32_t slot = ring_a + j * kSlotBytes;
-                    uint64_t a[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) a[i] = make_smem_desc(slot + i * kA2ArrBytes, 2048, 128);
-                    const uint32_t koff = static_cast<uint32_t>(j) * 2 * 2048;       // 16 n = 2 K-groups
-                    const uint64_t reH = make_smem_desc(b2_a + 0 * kB2ArrBytes + koff, 2048, 128);
-                    const uint64_t reL = make_smem_desc(b2_a + 1 * kB2ArrBytes + koff, 2048, 128);
-                    const uint64_t imH = make_smem_desc(b2_a + 2 * kB2ArrBytes + koff, 2048, 128);
-                    const uint64_t imL = make_smem_desc(b2_a + 3 * kB2ArrBytes + koff, 2048, 128);
+                __syncwarp();
+            }
+            // ---------------- stage 2: 4 K-chunks of 16 columns (n), even and odd outputs
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                mbar_wait(&full2[j], it & 1);
+                tc_fence_after();
+                if (elect_one()) {
+                    const uint64_t a = dA2 + j * kSlotStep;            // real hi, real lo, imag hi, imag lo of E then O
+                    const uint64_t bre = dB2 + j * ((2 * 2048) >> 4);  // 16 n = 2 K-groups
+                    const uint64_t bim = bre + 2 * kB2Step;
                     const uint32_t acc = (j > 0) ? 1u : 0u;
 #pragma unroll
                     for (int par = 0; par < 2; ++par) {
-                        // a[4 par + {0,1,2,3}] = real hi, real lo, imag hi, imag lo of E (par 0) / O (par 1)
-                        const uint32_t d = tmem + 256 + 128 * par;
-                        umma_f16(d, a[4 * par + 0], reH, idesc2, acc);
-                        umma_f16(d, a[4 * par + 1], reH, idesc2, 1u);
-                        umma_f16(d, a[4 * par + 0], reL, idesc2, 1u);
-                        umma_f16(d, a[4 * par + 2], imH, idesc2, 1u);
-                        umma_f16(d, a[4 * par + 3], imH, idesc2, 1u);
-                        umma_f16(d, a[4 * par + 2], imL, idesc2, 1u);
+                        const uint32_t d = 256 + 128 * par;
+                        const uint64_t ap = a + 4 * par * kA2Step;
+                        umma_f16(d, ap, bre, idesc2, acc);
+                        umma_f16(d, ap + kA2Step, bre, idesc2, 1u);
+                        umma_f16(d, ap, bre + kB2Step, idesc2, 1u);
+                        umma_f16(d, ap + 2 * kA2Step, bim, idesc2, 1u);
+                        umma_f16(d, ap + 3 * kA2Step, bim, idesc2, 1u);
+                        umma_f16(d, ap + 2 * kA2Step, bim + kB2Step, idesc2, 1u);
                     }
+                    if (j == 3) umma_commit(d2_full);
                 }
-                umma_commit(d2_full);
+                __syncwarp();
             }
         }
     }

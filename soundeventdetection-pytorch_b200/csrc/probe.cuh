@@ -74,4 +74,69 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const float* __restr
     }
 }
 
+
+// tcgen05.mma throughput probe: every CTA issues `reps` MMAs of 128 x N x 16 (K-major or MN-major B, no swizzle)
+// round-robin over `n_acc` accumulator tiles and reports cycles per MMA (block 0) in out[0].
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(unsigned long long* out, int N, int b_major, int n_acc,
+                                                           int reps, int lbo_a, int lbo_b) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_ptr;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    for (int i = tid; i < 64 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    if (warp == 0) tmem_alloc<512>(&tmem_ptr);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_ptr;
+    const int mode = lbo_b >> 24;          // 0: lane-0 branch, 1: converged warp + elect
+    lbo_b &= 0xffffff;
+    if (mode == 0) {
+        if (tid == 0) {
+            const uint32_t idesc = make_idesc(kFmtF16, kMajorK, b_major, 128, N);
+            const uint64_t da = make_smem_desc(smem_u32(smem), lbo_a, 128);
+            const uint64_t db = make_smem_desc(smem_u32(smem) + 32768, lbo_b, 128);
+            const long long t0 = clock64();
+            for (int r = 0; r < reps; ++r) umma_f16(tmem + (r % n_acc) * (512 / 4), da + (r & 7) * 16, db, idesc, 1u);
+            umma_commit(&bar);
+            mbar_wait(&bar, 0);
+            const long long t1 = clock64();
+            if (blockIdx.x == 0) out[0] = static_cast<unsigned long long>(t1 - t0);
+        }
+    } else if (warp == 1) {
+        // converged warp, uniform operands (the 512-column allocation always starts at TMEM address 0), one elected
+        // lane issues
+        if (tmem != 0) __trap();
+        const uint32_t idesc = make_idesc(kFmtF16, kMajorK, b_major, 128, N);
+        const uint64_t da = make_smem_desc(smem_u32(smem), lbo_a, 128);
+        const uint64_t db = make_smem_desc(smem_u32(smem) + 32768, lbo_b, 128);
+        const uint32_t amask = (n_acc >= 4) ? 3u : (n_acc >= 2 ? 1u : 0u);
+        const long long t0 = clock64();
+        for (int r = 0; r < reps; r += 4) {
+            if (elect_one()) {
+                umma_f16(((r + 0) & amask) * 128, da, db, idesc, 1u);
+                umma_f16(((r + 1) & amask) * 128, da + 16, db, idesc, 1u);
+                umma_f16(((r + 2) & amask) * 128, da + 32, db, idesc, 1u);
+                umma_f16(((r + 3) & amask) * 128, da + 48, db, idesc, 1u);
+            }
+            __syncwarp();
+        }
+        if (elect_one()) umma_commit(&bar);
+        __syncwarp();
+        mbar_wait(&bar, 0);
+        const long long t1 = clock64();
+        if (blockIdx.x == 0 && (tid & 31) == 0) out[0] = static_cast<unsigned long long>(t1 - t0);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem);
+    }
+}
+
 }  // namespace sedb

@@ -19,7 +19,8 @@ namespace {
 
 thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
-unsigned long long* g_prof = nullptr;   // device buffer of 16 counters when phase profiling is enabled
+unsigned long long* g_prof = nullptr;   // device buffer of 8 x 16 counters when phase profiling is enabled
+int g_conv_layer = 0;
 
 int fail(const char* fmt, ...) {
     char buf[512];
@@ -309,15 +310,29 @@ int sedb_sed_host_f32(sedb_ctx_t* ctx, sedb_cnn_t* cnn, const float* wave_host, 
     return run_host_pipeline(ctx, cnn, wave_host, n_clips, n_samples, wave_stride, norm_host, probs_host);
 }
 
+int sedb_debug_umma_rate(int N, int b_major, int n_acc, int reps, int lbo_a, int lbo_b, int grid,
+                         unsigned long long* cycles_host) {
+    if (!cycles_host || N < 16 || N > 128 || n_acc < 1 || n_acc > 4 || reps < 1) return fail("bad arguments");
+    unsigned long long* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 8));
+    CUDA_TRY(cudaFuncSetAttribute(sedb::umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    sedb::umma_rate_kernel<<<grid, 128, 64 * 1024>>>(d, N, b_major, n_acc, reps, lbo_a, lbo_b);
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(cycles_host, d, 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return 0;
+}
+
 int sedb_debug_phase_profile(int enable, unsigned long long* out_host16) {
+    g_conv_layer = 0;
     if (enable && !g_prof) {
-        CUDA_TRY(cudaMalloc(&g_prof, 16 * sizeof(unsigned long long)));
-        CUDA_TRY(cudaMemset(g_prof, 0, 16 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMalloc(&g_prof, 128 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemset(g_prof, 0, 128 * sizeof(unsigned long long)));
     }
     if (out_host16 && g_prof) {
         CUDA_TRY(cudaDeviceSynchronize());
-        CUDA_TRY(cudaMemcpy(out_host16, g_prof, 16 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        CUDA_TRY(cudaMemset(g_prof, 0, 16 * sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemcpy(out_host16, g_prof, 128 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        CUDA_TRY(cudaMemset(g_prof, 0, 128 * sizeof(unsigned long long)));
     }
     if (!enable && g_prof) {
         cudaFree(g_prof);

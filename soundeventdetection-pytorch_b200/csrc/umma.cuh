@@ -81,6 +81,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// One elected lane of a fully converged warp.  Code that issues tcgen05.mma / bulk copies should keep the whole warp
+// converged and guard only the instruction with this predicate: operands then stay in uniform registers, whereas a
+// lane-divergent `if (lane == 0)` region makes ptxas wrap every UTCHMMA in an R2UR + vote loop (~150 cycles per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // ------------------------------------------------------------------ proxy fences
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() {

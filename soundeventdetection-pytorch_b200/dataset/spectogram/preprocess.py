@@ -131,3 +131,116 @@ def calculate_scalar_of_tensor(x):
         return x.mean(dim=dims), x.std(dim=dims, unbiased=False)
     axis = 0 if x.ndim == 2 else (0, 1)
     return np.mean(x, axis=axis), np.std(x, axis=axis)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Callers of the hot path: offline feature extraction and the dataset transform, batched on
+# the device.
+def transform(x, mean, std, preprocessed_mode='logMel'):
+    """Batched ``SpectogramDataset.transform`` (reference spectograms_dataset.py:104-110).
+
+    ``logMel`` mode: ``(x - mean) / std`` with per-mel-bin statistics.  ``Complex`` mode: the complex STFT is normalised
+    per FFT bin (complex mean, real std) and then converted with :func:`multichannel_complex_to_log_mel` -- one kernel
+    call per batch instead of one NumPy call per sample inside DataLoader workers.
+    """
+    if preprocessed_mode not in ('logMel', 'Complex'):
+        raise ValueError("Spectogram type should be either logmel or complex")
+    is_np = not isinstance(x, torch.Tensor)
+    xt = torch.from_numpy(np.ascontiguousarray(x)).cuda() if is_np else x
+    m = torch.as_tensor(np.asarray(mean) if not isinstance(mean, torch.Tensor) else mean).to(xt.device)
+    s = torch.as_tensor(np.asarray(std) if not isinstance(std, torch.Tensor) else std).to(xt.device)
+    y = (xt - m) / s
+    if preprocessed_mode == 'Complex':
+        y = multichannel_complex_to_log_mel(y.to(torch.complex64))
+    return y.cpu().numpy() if is_np else y
+
+
+def preprocess_data(audio_path_and_labels, output_dir, output_mean_std_file, preprocess_mode='logMel',
+                    read_audio=None, batch_files=16):
+    """Drop-in for the reference's ``preprocess_data`` (preprocess.py:60-81), batched through the fused kernel.
+
+    Writes, per file, ``<audio_name>_<mode>_features_and_labels.pkl`` = ``{'features', 'start_times', 'end_times'}``
+    with ``features`` a ``(C, T, 64)`` float32 log-mel (or ``(C, T, 16385)`` complex64 STFT in ``Complex`` mode) and the
+    dataset-wide ``{'mean', 'std'}`` pickle (per feature bin over all channels and frames) -- the same on-disk format, so
+    the reference's ``SpectogramDataset`` loads the result unchanged.  ``read_audio(path) -> (samples, channels)``
+    defaults to the reference's ``read_multichannel_audio`` (needs ``soundfile``); files of equal length are processed
+    ``batch_files`` at a time.  The debug plot of the reference (preprocess.py:83-86) is not produced.
+    """
+    import os
+    import pickle
+
+    if read_audio is None:
+        try:
+            import soundfile  # noqa: F401
+        except ImportError as e:                      # pragma: no cover - depends on the host
+            raise RuntimeError("preprocess_data needs `soundfile` to decode audio (or pass read_audio=...)") from e
+        read_audio = _read_multichannel_audio
+    os.makedirs(output_dir, exist_ok=True)
+    n_feat = cfg.mel_bins if preprocess_mode == 'logMel' else NUM_BINS
+    s1 = torch.zeros(n_feat, dtype=torch.float64, device="cuda")     # per-bin running sums (complex handled apart)
+    s2 = torch.zeros(n_feat, dtype=torch.float64, device="cuda")
+    s1c = torch.zeros(n_feat, dtype=torch.complex128, device="cuda")
+    count = 0
+
+    def flush(group):
+        nonlocal s1, s2, s1c, count
+        waves = [g[0] for g in group]
+        C = waves[0].shape[1]
+        stacked = torch.from_numpy(np.ascontiguousarray(np.stack([w.T for w in waves]), dtype=np.float32)).cuda()
+        flat = stacked.reshape(len(waves) * C, -1)                   # one mono "clip" per (file, channel)
+        if preprocess_mode == 'logMel':
+            feats = waveform_to_log_mel(flat)
+            f64 = feats.to(torch.float64)
+            s1 += f64.sum((0, 1))
+            s2 += (f64 * f64).sum((0, 1))
+        else:
+            feats = multichannel_stft(flat.t().contiguous())         # (files * C, T, 16385) complex64 on the device
+            f = feats.to(torch.complex128)
+            s1c += f.sum((0, 1))
+            s2 += (f.real ** 2 + f.imag ** 2).sum((0, 1))
+        count += feats.shape[0] * feats.shape[1]
+        feats = feats.reshape(len(waves), C, feats.shape[-2], feats.shape[-1]).cpu().numpy()
+        for (wave, start_times, end_times, audio_name), feature in zip(group, feats):
+            path = os.path.join(output_dir, audio_name + f"_{preprocess_mode}_features_and_labels.pkl")
+            with open(path, 'wb') as fh:
+                pickle.dump({'features': feature, 'start_times': start_times, 'end_times': end_times}, fh)
+
+    group = []
+    for (audio_path, start_times, end_times, audio_name) in audio_path_and_labels:
+        wave = np.asarray(read_audio(audio_path))
+        if group and (wave.shape != group[0][0].shape or len(group) >= batch_files):
+            flush(group)
+            group = []
+        group.append((wave, start_times, end_times, audio_name))
+    if group:
+        flush(group)
+
+    if preprocess_mode == 'logMel':
+        mean = s1 / count
+        std = torch.sqrt(torch.clamp(s2 / count - mean * mean, min=0.0))
+        mean_np, std_np = mean.cpu().numpy(), std.cpu().numpy()
+    else:                                             # np.mean / np.std of a complex array: complex mean, real std
+        mean_c = s1c / count
+        std = torch.sqrt(torch.clamp(s2 / count - (mean_c.real ** 2 + mean_c.imag ** 2), min=0.0))
+        mean_np, std_np = mean_c.cpu().numpy(), std.cpu().numpy()
+    with open(output_mean_std_file, 'wb') as fh:
+        pickle.dump({'mean': mean_np, 'std': std_np}, fh)
+    return mean_np, std_np
+
+
+def _read_multichannel_audio(audio_path, target_fs=None):
+    """Reference ``read_multichannel_audio`` (dataset_utils.py:63-86) for files already at the working sample rate:
+    decode with soundfile, downmix to ``audio_channels`` by averaging.  Resampling is out of scope."""
+    import soundfile
+    audio, sample_rate = soundfile.read(audio_path)
+    if audio.ndim == 1:
+        audio = audio.reshape(-1, 1)
+    if audio.shape[1] < cfg.audio_channels:
+        audio = np.repeat(audio.mean(1).reshape(-1, 1), cfg.audio_channels, axis=1)
+    elif cfg.audio_channels == 1:
+        audio = audio.mean(1).reshape(-1, 1)
+    elif audio.shape[1] > cfg.audio_channels:
+        audio = audio[:, :cfg.audio_channels]
+    if sample_rate != cfg.working_sample_rate:
+        raise RuntimeError(f"{audio_path}: sample rate {sample_rate} != {cfg.working_sample_rate}; resample first")
+    return audio

@@ -13,7 +13,7 @@ torch.cuda.synchronize()
 lib.sedb_debug_phase_profile(1, None)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); P.waveform_to_log_mel(w); e1.record(); torch.cuda.synchronize()
-out = np.zeros(16, dtype=np.uint64)
+out = np.zeros(128, dtype=np.uint64)
 lib.sedb_debug_phase_profile(0, ctypes.c_void_p(out.ctypes.data))
 frames = B * 182
 names = ["load+scale", "fold/split", "wait S1", "twiddle/radix2", "wait S2", "power", "row128", "final sync", "sync->mel", "mel partials", "sync", "finalize"]
