@@ -112,6 +112,16 @@ size_t sedb_m5_workspace_bytes(const sedb_m5_t* m5, long long n_frames);
 int sedb_m5_forward(sedb_m5_t* m5, const float* x_dev, long long n_frames, float* logits_dev,
                     void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---- training step support (train.py:85,101-103) ------------------------------------------------------------ */
+/* One fused optimizer update over a flat float32 parameter buffer with the semantics of
+ * torch.optim.Adam(lr, betas, eps, weight_decay, amsgrad=True) as constructed at train.py:85:
+ *   g = grad * grad_scale (+ weight_decay * p);  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  vmax = max(vmax, v)
+ *   p -= lr / (1 - b1^step) * m / (sqrt(vmax) / sqrt(1 - b2^step) + eps)
+ * grad_scale folds the 1/world_size of the data-parallel gradient mean into the update; step counts from 1. */
+int sedb_adam_amsgrad_step(float* param_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                           float* max_exp_avg_sq_dev, long long n, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, long long step, float grad_scale, void* stream);
+
 /* ---- end-to-end: waveform -> log-mel -> CNN -> frame probabilities -------------------------------- */
 /* infer.py:27-33 intent.  wave_host: [n_clips, wave_stride] float32 host; probs_host: [n_clips, out_frames,
  * classes] float32 host.  H2D chunks, log-mel, CNN and the D2H of the probabilities are pipelined. */

@@ -48,6 +48,8 @@ _SIGNATURES = {
     "sedb_m5_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, c_ll]),
     "sedb_m5_forward": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_ll, c_float_p, ctypes.c_void_p,
                                        ctypes.c_size_t, ctypes.c_void_p]),
+    "sedb_adam_amsgrad_step": (ctypes.c_int, [c_float_p] * 5 + [c_ll] + [ctypes.c_float] * 5 + [c_ll, ctypes.c_float,
+                                                                                                ctypes.c_void_p]),
     "sedb_sed_host_f32": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_float_p, c_ll, c_ll, c_ll, c_float_p,
                                          c_float_p]),
     "sedb_debug_umma_probe": (ctypes.c_int, [c_float_p, c_float_p, c_float_p] + [ctypes.c_int] * 7

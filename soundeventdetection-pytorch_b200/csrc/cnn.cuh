@@ -563,6 +563,29 @@ __global__ void __launch_bounds__(256) head1d_kernel(const uint8_t* __restrict__
     }
 }
 
+// ---- optimizer -----------------------------------------------------------------------------------------
+// torch.optim.Adam(amsgrad=True) over a flat buffer (train.py:85); HBM-bound: 20 B read + 16 B written per parameter.
+__global__ void __launch_bounds__(256) adam_amsgrad_kernel(float* __restrict__ p, const float* __restrict__ g,
+                                                           float* __restrict__ m, float* __restrict__ v,
+                                                           float* __restrict__ vmax, long long n, float step_size,
+                                                           float beta1, float beta2, float inv_bc2_sqrt, float eps,
+                                                           float weight_decay, float grad_scale) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const float pi = p[i];
+        float gi = g[i] * grad_scale;
+        if (weight_decay != 0.f) gi = fmaf(weight_decay, pi, gi);
+        const float mi = fmaf(beta1, m[i], (1.0f - beta1) * gi);          // lerp(m, g, 1 - b1)
+        const float vi = fmaf(beta2, v[i], (1.0f - beta2) * gi * gi);
+        const float vm = fmaxf(vmax[i], vi);
+        m[i] = mi;
+        v[i] = vi;
+        vmax[i] = vm;
+        const float denom = sqrtf(vm) * inv_bc2_sqrt + eps;
+        p[i] = pi - step_size * (mi / denom);
+    }
+}
+
 // ---- parameter preparation ---------------------------------------------------------------------------
 // BN fold: scale = gamma / sqrt(var + eps), shift = beta - mean*scale (+ bias*scale)
 __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,

@@ -310,6 +310,26 @@ int sedb_sed_host_f32(sedb_ctx_t* ctx, sedb_cnn_t* cnn, const float* wave_host, 
     return run_host_pipeline(ctx, cnn, wave_host, n_clips, n_samples, wave_stride, norm_host, probs_host);
 }
 
+int sedb_adam_amsgrad_step(float* param_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                           float* max_exp_avg_sq_dev, long long n, float lr, float beta1, float beta2, float eps,
+                           float weight_decay, long long step, float grad_scale, void* stream) {
+    if (n < 0 || step < 1) return fail("sedb_adam_amsgrad_step: bad size or step");
+    if (n == 0) return 0;
+    if (!param_dev || !grad_dev || !exp_avg_dev || !exp_avg_sq_dev || !max_exp_avg_sq_dev) return fail("null buffer");
+    const double bc1 = 1.0 - std::pow(static_cast<double>(beta1), static_cast<double>(step));
+    const double bc2 = 1.0 - std::pow(static_cast<double>(beta2), static_cast<double>(step));
+    const float step_size = static_cast<float>(static_cast<double>(lr) / bc1);
+    const float inv_bc2_sqrt = static_cast<float>(1.0 / std::sqrt(bc2));
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    sedb::adam_amsgrad_kernel<<<static_cast<int>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        param_dev, grad_dev, exp_avg_dev, exp_avg_sq_dev, max_exp_avg_sq_dev, n, step_size, beta1, beta2, inv_bc2_sqrt,
+        eps, weight_decay, grad_scale);
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
 int sedb_debug_umma_rate(int N, int b_major, int n_acc, int reps, int lbo_a, int lbo_b, int grid,
                          unsigned long long* cycles_host) {
     if (!cycles_host || N < 16 || N > 128 || n_acc < 1 || n_acc > 4 || reps < 1) return fail("bad arguments");

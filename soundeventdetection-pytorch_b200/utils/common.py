@@ -15,3 +15,25 @@ def human_format(num):
 
 def count_parameters(model):
     return sum(p.numel() for p in model.parameters() if p.requires_grad)
+
+
+class WeightedBCE:
+    """Binary cross-entropy on logits with a positive-class weight (the reference's loss, utils/common.py:11-30).
+
+    ``multi_frame=True``: output/target are (batch, frames, classes) and are cropped to their common number of frames
+    (pooling can shorten the output); otherwise the output is flattened to (batch,).
+    """
+
+    def __init__(self, recall_factor, multi_frame):
+        import torch
+        self.recall_factor = torch.tensor([float(recall_factor)])
+        self.multi_frame = multi_frame
+
+    def __call__(self, output, target):
+        from torch.nn.functional import binary_cross_entropy_with_logits
+        if self.multi_frame:
+            n = min(output.shape[1], target.shape[1])
+            output, target = output[:, :n], target[:, :n]
+        else:
+            output = output.reshape(-1)
+        return binary_cross_entropy_with_logits(output, target, pos_weight=self.recall_factor.to(output.device))

@@ -41,3 +41,32 @@ def test_two_rank_sharding_and_gather():
     full = ret["full"]
     assert full.shape == (n_clips, 4, 1)
     assert torch.equal(full[:, 0, 0], torch.arange(n_clips, dtype=torch.float32))
+
+
+def _grad_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    import sed_b200  # noqa: F401
+    from sed_b200 import parallel
+    from sed_b200.train import FlatBuffers, allreduce_sum_
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    parallel.init_process_group("gloo")
+    torch.manual_seed(0)                                   # same replica on every rank
+    net = torch.nn.Sequential(torch.nn.Linear(8, 4), torch.nn.ReLU(), torch.nn.Linear(4, 1))
+    flat = FlatBuffers(net)
+    x = torch.full((3, 8), float(rank + 1))
+    net(x).sum().backward()                                # gradients land in the flat bucket
+    local = flat.grad.clone()
+    allreduce_sum_(flat.grad)                              # the ONE collective of a step
+    ret[rank] = (local, flat.grad.clone(), flat.numel)
+    dist.destroy_process_group()
+
+
+def test_two_rank_single_bucket_gradient_allreduce():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_grad_worker, args=(2, 29641, ret), nprocs=2, join=True)
+    (l0, s0, n0), (l1, s1, n1) = ret[0], ret[1]
+    assert n0 == n1 == 8 * 4 + 4 + 4 + 1
+    assert torch.allclose(s0, l0 + l1) and torch.equal(s0, s1)
+    assert not torch.equal(l0, l1)
