@@ -162,25 +162,36 @@ __device__ __forceinline__ void mel_partials(const float* __restrict__ p_s, cons
         part_s[kMelMaxPieces + i] = s1;
     }
 }
-// threads 0..63: combine the moments of segments tid and tid+1 into filter `tid`, convert to dB, normalise, store.
+// TPF threads per filter (64 * TPF threads in total): thread (m, sub) adds every TPF-th partial slot of segments m and
+// m+1, the TPF lanes are combined with a fixed shuffle tree, and lane sub == 0 converts to dB, normalises and stores.
+template <int TPF>
 __device__ __forceinline__ void mel_finalize(const float* __restrict__ part_s, const int4* __restrict__ tab_s,
                                              const float* __restrict__ coef_s, const float* __restrict__ norm,
                                              float inv_scale2, float* __restrict__ out_row, int tid) {
-    if (tid < kMel) {
-        float m0[2] = {0.f, 0.f}, m1[2] = {0.f, 0.f};
+    const int m = tid / TPF, sub = tid % TPF;
+    float m0[2] = {0.f, 0.f}, m1[2] = {0.f, 0.f};
+#pragma unroll
+    for (int d = 0; d < 2; ++d) {
+        const int4 f = tab_s[kMelMaxPieces / 2 + m + d];
+        for (int i = sub; i < f.y; i += TPF) {
+            m0[d] += part_s[f.x + i];
+            m1[d] += part_s[kMelMaxPieces + f.x + i];
+        }
+    }
+#pragma unroll
+    for (int o = 1; o < TPF; o <<= 1) {
 #pragma unroll
         for (int d = 0; d < 2; ++d) {
-            const int4 f = tab_s[kMelMaxPieces / 2 + tid + d];
-            for (int i = 0; i < f.y; ++i) {
-                m0[d] += part_s[f.x + i];
-                m1[d] += part_s[kMelMaxPieces + f.x + i];
-            }
+            m0[d] += __shfl_xor_sync(0xffffffffu, m0[d], o);
+            m1[d] += __shfl_xor_sync(0xffffffffu, m1[d], o);
         }
-        const float4 cf = reinterpret_cast<const float4*>(coef_s)[tid];
+    }
+    if (sub == 0) {
+        const float4 cf = reinterpret_cast<const float4*>(coef_s)[m];
         const float a = fmaf(cf.x, m1[0], cf.y * m0[0]) + fmaf(cf.z, m1[1], cf.w * m0[1]);
         float db = 10.0f * log10f(fmaxf(1e-10f, a * inv_scale2));        // librosa.power_to_db(ref=1, amin=1e-10)
-        if (norm != nullptr) db = (db - norm[tid]) / norm[kMel + tid];   // spectograms_dataset.py:105
-        out_row[tid] = db;
+        if (norm != nullptr) db = (db - norm[m]) / norm[kMel + m];       // spectograms_dataset.py:105
+        out_row[m] = db;
     }
 }
 
@@ -550,12 +561,38 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 if (lane == 0) mbar_arrive(&full2[c]);
             }
             SEDB_PROF(3);   // twiddle / radix-2 / split
+            // row k1 = 128 while the stage-2 MMAs drain: X[128 + 256 k2] = sum_n2 Y[n2,128] exp(-2 pi i n2 (2 k2+1)/256),
+            // k2 in [0,64).  The power goes to the spectrum after d2_full (it aliases the operand ring until then).
+            float2* spec_row = nullptr;
+            if (MODE == 1) spec_row = prm.spec + (static_cast<long long>(clip) * prm.n_frames + t) * kBins;
+            worker_sync();                                            // v_s (written by warps 0-3) visible
+            float p128 = 0.f;
+            {
+                const int k2 = tid >> 3;
+                const int part = tid & 7;
+                float ar = 0.f, ai = 0.f;
+                const int mm = 2 * k2 + 1;
+#pragma unroll 8
+                for (int i = 0; i < 16; ++i) {
+                    const int n2 = part + 8 * i;                      // interleaved: table reads spread over banks
+                    const float2 w = cs_s[(n2 * mm) & 255];
+                    const float v = v_s[n2];
+                    ar = fmaf(v, w.x, ar);
+                    ai = fmaf(v, w.y, ai);
+                }
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    ar += __shfl_xor_sync(0xffffffffu, ar, o);
+                    ai += __shfl_xor_sync(0xffffffffu, ai, o);
+                }
+                p128 = ar * ar + ai * ai;
+                if (MODE == 1 && part == 0) spec_row[128 + 256 * k2] = make_float2(ar * inv_scale, ai * inv_scale);
+            }
+            SEDB_PROF(6);   // row 128
             // ---------------------------------------------------------------- power spectrum / complex output
             mbar_wait(d2_full, it & 1);
             tc_fence_after();
             SEDB_PROF(4);   // wait for stage-2 MMAs
-            float2* spec_row = nullptr;
-            if (MODE == 1) spec_row = prm.spec + (static_cast<long long>(clip) * prm.n_frames + t) * kBins;
             const bool mirrored = (sub >= 2);                         // k2 = 2 j + par >= 64
 #pragma unroll 1
             for (int hb = 0; hb < 2; ++hb) {
@@ -581,33 +618,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                     }
                 }
             }
+            if (MODE == 0 && (tid & 7) == 0) p_s[128 + 256 * (tid >> 3)] = p128;
             SEDB_PROF(5);   // power spectrum
-            // row k1 = 128: X[128 + 256 k2] = sum_n2 Y[n2,128] exp(-2 pi i n2 (2 k2 + 1)/256), k2 in [0,64)
-            worker_sync();                                            // v_s (written by warps 0-3) visible
-            {
-                const int k2 = tid >> 3;
-                const int part = tid & 7;
-                float ar = 0.f, ai = 0.f;
-                const int mm = 2 * k2 + 1;
-#pragma unroll 8
-                for (int i = 0; i < 16; ++i) {
-                    const int n2 = part + 8 * i;                      // interleaved: table reads spread over banks
-                    const float2 w = cs_s[(n2 * mm) & 255];
-                    const float v = v_s[n2];
-                    ar = fmaf(v, w.x, ar);
-                    ai = fmaf(v, w.y, ai);
-                }
-#pragma unroll
-                for (int o = 1; o < 8; o <<= 1) {
-                    ar += __shfl_xor_sync(0xffffffffu, ar, o);
-                    ai += __shfl_xor_sync(0xffffffffu, ai, o);
-                }
-                if (part == 0) {
-                    if (MODE == 0) p_s[128 + 256 * k2] = ar * ar + ai * ai;
-                    else spec_row[128 + 256 * k2] = make_float2(ar * inv_scale, ai * inv_scale);
-                }
-            }
-            SEDB_PROF(6);   // row 128
             tc_fence_before();
             if (MODE == 0) {
                 if (tid < 3) p_s[kBins + tid] = 0.f;                  // padding read by the vectorised mel bands
@@ -617,14 +629,17 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 SEDB_PROF(9);
                 worker_sync();
                 SEDB_PROF(10);
+                if (lane == 0) mbar_arrive(ring_free);               // p_s is dead: the ring may be refilled
                 float* out_row = prm.out + (static_cast<long long>(clip) * prm.n_frames + t) * kMel;
-                mel_finalize(part_s, mel_tab_s, coef_s, prm.norm != nullptr ? norm_s : nullptr, inv_scale * inv_scale,
-                             out_row, tid);
+                mel_finalize<kWorkerThreads / kMel>(part_s, mel_tab_s, coef_s, prm.norm != nullptr ? norm_s : nullptr,
+                                                    inv_scale * inv_scale, out_row, tid);
                 SEDB_PROF(11);
             }
-            worker_sync();                                            // ring (aliased by p_s) may be refilled
+            if (MODE != 0) {
+                worker_sync();                                        // stores of this frame done
+                if (lane == 0) mbar_arrive(ring_free);
+            }
             SEDB_PROF(7);   // mel + dB
-            if (lane == 0) mbar_arrive(ring_free);
         }
     }
 
@@ -661,7 +676,7 @@ __global__ void __launch_bounds__(256) power_mel_db_kernel(const float2* __restr
         __syncthreads();
         mel_partials(p_s, mel_tab_s, part_s, tid, 256);
         __syncthreads();
-        mel_finalize(part_s, mel_tab_s, coef_s, norm, 1.0f, out + row * kMel, tid);
+        mel_finalize<256 / kMel>(part_s, mel_tab_s, coef_s, norm, 1.0f, out + row * kMel, tid);
         __syncthreads();
     }
 }
