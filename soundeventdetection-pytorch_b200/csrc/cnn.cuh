@@ -464,75 +464,184 @@ __global__ void __launch_bounds__(256) head2d_kernel(const uint8_t* __restrict__
 }
 
 // ------------------------------------------------------------------------------------------------------
-// M5 conv_block1 (waveform_models.py:14-19): Conv1d(1->64, k=79, s=4, p=39) + BN + ReLU + MaxPool1d(4), CUDA
-// cores, fp32.  grid = (tiles of kIn1dTile pooled positions, frames); one warp per pooled position, each lane
-// owns two output channels.  Writes blocked planes (C = 64).
-constexpr int kIn1dTile = 64;
-constexpr int kIn1dSeg = 16 * kIn1dTile + 80;                         // input samples needed by one tile
-constexpr int kIn1dSmem = (79 * 64 + kIn1dSeg + 128) * 4;
+// M5 conv_block1 on tensor cores: Conv1d(1->64, k=79, s=4, p=39) + BN + ReLU + MaxPool1d(4)
+// (waveform_models.py:14-19).  GEMM view: M = output positions, K = 80 taps (79 + one zero), N = 64 channels.
+// The im2col matrix A[p, j] = x[4p - 39 + j] is never built: the samples of a tile are staged once in shared memory
+// as bf16 hi/lo, and the tcgen05 K-major descriptor walks them with OVERLAPPING strides -- 16 bytes (8 samples)
+// between consecutive rows and 16 bytes between the two K-groups of an MMA.  A 16-byte row pitch is a conv stride of
+// 8 samples, so even and odd output positions form two interleaved GEMMs (parity r reads a copy of the samples shifted
+// by 4r), whose accumulators are max-combined in the epilogue as the first half of the MaxPool.
+// One work item = 256 consecutive positions of one frame (64 pooled positions); 8 worker warps stage + drain, one
+// warp issues; staging and TMEM accumulators are double buffered.
+constexpr int kFrontThreads = 288;
+constexpr int kFrontTilePos = 256;
+constexpr int kFrontSamples = 1120;                        // per parity: 8*127 + 80 = 1096 halves, padded
+constexpr int kFrontStageBytes = 4 * kFrontSamples * 2;    // {parity 0, parity 1} x {hi, lo}
+constexpr int kFrontWBytes = 2 * 64 * 80 * 2;              // weights hi | lo, canonical K-major [64][80]
+constexpr int kFrontSmem = 2 * kFrontStageBytes + kFrontWBytes + 2 * 64 * 4 + 16 * 8 + 16 + 128;
 
-__global__ void __launch_bounds__(256) conv_in1d_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                        const float* __restrict__ scale, const float* __restrict__ shift,
-                                                        uint8_t* __restrict__ out, int L_in, int L_out, int S_out) {
+__global__ void __launch_bounds__(kFrontThreads, 1) m5_front_kernel(const float* __restrict__ x,
+                                                                    const uint8_t* __restrict__ wpack,
+                                                                    const float* __restrict__ scale,
+                                                                    const float* __restrict__ shift,
+                                                                    uint8_t* __restrict__ out, int n_frames, int L_in,
+                                                                    int L_conv, int L_out, int S_out) {
     extern __shared__ __align__(128) uint8_t smem[];
-    float* w_s = reinterpret_cast<float*>(smem);          // [79][64]  (tap-major: lanes read consecutive channels)
-    float* x_s = w_s + 79 * 64;                           // [kIn1dSeg]
-    float* sc_s = x_s + kIn1dSeg;
+    uint8_t* stage = smem;                                          // [2 buffers][parity][hi|lo][kFrontSamples] bf16
+    uint8_t* w_s = smem + 2 * kFrontStageBytes;
+    float* sc_s = reinterpret_cast<float*>(w_s + kFrontWBytes);
     float* sh_s = sc_s + 64;
+    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(sh_s + 64) + 15) & ~static_cast<uintptr_t>(15));
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* full = bars + 0;       // [2] staging buffer filled (8 warps)
+    uint64_t* acc_full = bars + 2;   // [2] accumulators complete (commit)
+    uint64_t* epi_done = bars + 4;   // [2] accumulators drained (8 warps)
+
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int frame = blockIdx.y;
-    const int j0 = blockIdx.x * kIn1dTile;
-    for (int i = tid; i < 79 * 64; i += 256) {
-        const int c = i / 79, t = i % 79;
-        w_s[t * 64 + c] = w[i];
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&full[i], 8);
+            mbar_init(&acc_full[i], 1);
+            mbar_init(&epi_done[i], 8);
+        }
+        mbar_fence_init();
     }
+    if (warp == 8) tmem_alloc<512>(tmem_ptr_s);
+    for (int i = tid; i < kFrontWBytes / 16; i += kFrontThreads)
+        reinterpret_cast<uint4*>(w_s)[i] = reinterpret_cast<const uint4*>(wpack)[i];
     if (tid < 64) {
         sc_s[tid] = scale[tid];
         sh_s[tid] = shift[tid];
     }
-    const float* xf = x + static_cast<long long>(frame) * L_in;
-    const int x0 = 16 * j0 - 39;
-    for (int i = tid; i < kIn1dSeg; i += 256) {
-        const int g = x0 + i;
-        x_s[i] = (g >= 0 && g < L_in) ? __ldg(xf + g) : 0.f;
-    }
+    fence_proxy_async_smem();
+    tc_fence_before();
     __syncthreads();
-    const int c0 = 2 * lane;
-    const float s0 = sc_s[c0], s1 = sc_s[c0 + 1], b0 = sh_s[c0], b1 = sh_s[c0 + 1];
-    for (int jl = warp; jl < kIn1dTile; jl += 8) {
-        const int j = j0 + jl;
-        if (j >= L_out) break;
-        float a[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-        const float* xs = x_s + 16 * jl;
-#pragma unroll 4
-        for (int t = 0; t < 79; ++t) {
-            const float2 wv = *reinterpret_cast<const float2*>(w_s + t * 64 + c0);
+    tc_fence_after();
+    const uint32_t tmem = *tmem_ptr_s;
+
+    const int tiles_per_frame = (L_conv + kFrontTilePos - 1) / kFrontTilePos;
+    const long long total = static_cast<long long>(n_frames) * tiles_per_frame;
+    const int n_items = (blockIdx.x < total) ? static_cast<int>((total - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+
+    if (warp == 8) {
+        // ================================================================ MMA issuer (converged warp, elected lane)
+        if (tmem != 0) __trap();
+        const uint32_t idesc = make_idesc(kFmtBF16, kMajorK, kMajorK, 128, 64);
+        const uint64_t a_base = make_smem_desc(smem_u32(stage), 16, 128);          // rows 16 B apart, K-groups 16 B apart
+        const uint64_t b_base = make_smem_desc(smem_u32(w_s), 64 * 16, 128);
+        constexpr uint32_t kArr = (kFrontSamples * 2) >> 4;                          // one staged array, 16-byte units
+        constexpr uint32_t kWLo = (64 * 80 * 2) >> 4;
+        for (int it = 0; it < n_items; ++it) {
+            const int buf = it & 1;
+            if (it >= 2) {
+                mbar_wait(&epi_done[buf], ((it - 2) >> 1) & 1);
+                tc_fence_after();
+            }
+            mbar_wait(&full[buf], (it >> 1) & 1);
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-            for (int ps = 0; ps < 4; ++ps) {
-                const float xv = xs[4 * ps + t];
-                a[ps][0] = fmaf(xv, wv.x, a[ps][0]);
-                a[ps][1] = fmaf(xv, wv.y, a[ps][1]);
+                for (int r = 0; r < 2; ++r) {
+                    const uint64_t aH = a_base + buf * (4 * kArr) + r * (2 * kArr);
+                    const uint64_t aL = aH + kArr;
+                    const uint32_t d = buf * 128 + r * 64;
+#pragma unroll
+                    for (int ks = 0; ks < 5; ++ks) {
+                        const uint64_t bH = b_base + ks * ((2 * 64 * 16) >> 4);
+                        umma_f16(d, aH + 2 * ks, bH, idesc, ks > 0 ? 1u : 0u);      // 16 taps = 32 B further along each row
+                        umma_f16(d, aL + 2 * ks, bH, idesc, 1u);
+                        umma_f16(d, aH + 2 * ks, bH + kWLo, idesc, 1u);
+                    }
+                }
+                umma_commit(&acc_full[buf]);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================================================================ 8 worker warps: stage samples, drain tiles
+        const int q = warp & 3, grp = warp >> 2;               // TMEM lane quarter; channel half (32 channels)
+        auto stage_item = [&](int it) {
+            const long long item = blockIdx.x + static_cast<long long>(it) * gridDim.x;
+            const int frame = static_cast<int>(item / tiles_per_frame);
+            const int tile = static_cast<int>(item - static_cast<long long>(frame) * tiles_per_frame);
+            const float* xf = x + static_cast<long long>(frame) * L_in;
+            const int base = 4 * tile * kFrontTilePos - 39;   // sample index of tap 0 of the tile's first position
+            __nv_bfloat16* st = reinterpret_cast<__nv_bfloat16*>(stage + (it & 1) * kFrontStageBytes);
+            for (int i = tid; i < 2 * kFrontSamples; i += 256) {
+                const int r = i / kFrontSamples, k = i - r * kFrontSamples;
+                const int gi = base + 4 * r + k;
+                const float v = (gi >= 0 && gi < L_in) ? __ldg(xf + gi) : 0.f;
+                const __nv_bfloat16 h = __float2bfloat16_rn(v);
+                st[(2 * r + 0) * kFrontSamples + k] = h;
+                st[(2 * r + 1) * kFrontSamples + k] = __float2bfloat16_rn(v - __bfloat162float(h));
+            }
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[it & 1]);
+        };
+        if (n_items > 0) stage_item(0);
+        for (int it = 0; it < n_items; ++it) {
+            if (it + 1 < n_items) stage_item(it + 1);          // buffer (it+1)&1 was released by the MMAs of item it-1
+            const long long item = blockIdx.x + static_cast<long long>(it) * gridDim.x;
+            const int frame = static_cast<int>(item / tiles_per_frame);
+            const int tile = static_cast<int>(item - static_cast<long long>(frame) * tiles_per_frame);
+            const int buf = it & 1;
+            mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            tc_fence_after();
+            // lane = row qrow of the tile: positions 2 qrow (parity 0) and 2 qrow + 1 (parity 1); this warp handles
+            // channels [32 grp, 32 grp + 32)
+            const uint32_t t0 = tmem + (static_cast<uint32_t>(q * 32) << 16) + buf * 128 + 32 * grp;
+            float y[32];
+#pragma unroll
+            for (int h2 = 0; h2 < 2; ++h2) {
+                float a0[16], a1[16];
+                tmem_ld16(t0 + 16 * h2, a0);
+                tmem_ld16(t0 + 64 + 16 * h2, a1);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const int c = 32 * grp + 16 * h2 + i;
+                    const float v0 = fmaf(a0[i], sc_s[c], sh_s[c]), v1 = fmaf(a1[i], sc_s[c], sh_s[c]);
+                    y[16 * h2 + i] = fmaxf(0.f, fmaxf(v0, v1));                 // ReLU and the first pooling pair
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&epi_done[buf]);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) y[i] = fmaxf(y[i], __shfl_xor_sync(0xffffffffu, y[i], 1));   // rows 2g, 2g+1
+            const int qrow = q * 32 + lane;
+            const int j = tile * (kFrontTilePos / 4) + (qrow >> 1);               // pooled position
+            if ((lane & 1) == 0 && j < L_out) {
+                const long long v = kConvLead + 1 + j;
+                const long long img = static_cast<long long>(frame) * 2 * 8;
+#pragma unroll
+                for (int g2 = 0; g2 < 4; ++g2) {
+                    const int kg = 4 * grp + g2;
+                    store_split8(out + ((img + kg) * S_out + v) * 16, out + ((img + 8 + kg) * S_out + v) * 16, y + 8 * g2);
+                }
             }
         }
-        float y0 = 0.f, y1 = 0.f;                                    // ReLU output is >= 0
-#pragma unroll
-        for (int ps = 0; ps < 4; ++ps) {
-            y0 = fmaxf(y0, fmaf(a[ps][0], s0, b0));
-            y1 = fmaxf(y1, fmaf(a[ps][1], s1, b1));
-        }
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(y0), h1 = __float2bfloat16_rn(y1);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(y0 - __bfloat162float(h0));
-        const __nv_bfloat16 l1 = __float2bfloat16_rn(y1 - __bfloat162float(h1));
-        const long long v = kConvLead + 1 + j;
-        const long long img = static_cast<long long>(frame) * 2 * 8;
-        const int kg = lane >> 2, sub = (lane & 3) * 4;
-        uint8_t* hi = out + ((img + kg) * S_out + v) * 16 + sub;
-        uint8_t* lo = out + ((img + 8 + kg) * S_out + v) * 16 + sub;
-        *reinterpret_cast<uint32_t*>(hi) = static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&h0)) |
-                                           (static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&h1)) << 16);
-        *reinterpret_cast<uint32_t*>(lo) = static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&l0)) |
-                                           (static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(&l1)) << 16);
     }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) {
+        tc_fence_after();
+        tmem_dealloc<512>(tmem);
+    }
+}
+
+// Conv1d(1->64, k=79) weight [64][79] fp32 -> {hi, lo} x canonical K-major [64][80] bf16 (tap 79 = 0)
+__global__ void pack_front_weight_kernel(const float* __restrict__ w, uint8_t* __restrict__ out) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= 64 * 80) return;
+    const int c = idx / 80, k = idx % 80;
+    const float v = (k < 79) ? w[c * 79 + k] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    const int off = (k / 8) * (64 * 16) + c * 16 + (k % 8) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(out + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(out + 64 * 80 * 2 + off) = l;
 }
 
 // Head of M5 (waveform_models.py:66-67): mean over time, Linear.  One warp per frame.

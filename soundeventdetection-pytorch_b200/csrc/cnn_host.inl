@@ -243,7 +243,7 @@ static int cnn_make_plan(const sedb_cnn* m, long long n_clips, long long T, CnnP
 
 static int sedb_cnn_kernels_init() {
     CUDA_TRY(cudaFuncSetAttribute(sedb::conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(sedb::conv_in1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(sedb::m5_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sedb::kFrontSmem));
     return 0;
 }
 
@@ -429,6 +429,7 @@ struct sedb_m5 {
     sedb_ctx* ctx = nullptr;
     int classes = 0;
     float* w_in = nullptr;            // conv_block1 conv: [64][79]
+    uint8_t* w_front = nullptr;       // the same, packed bf16 hi|lo for m5_front_kernel
     float* scale_in = nullptr;
     float* shift_in = nullptr;
     std::vector<UmmaLayer> layers;    // the 8 k=3 convolutions
@@ -491,6 +492,7 @@ int sedb_m5_create(sedb_ctx_t* ctx, int classes_num, sedb_m5_t** out) {
     m->ctx = ctx;
     m->classes = classes_num;
     CUDA_TRY(cudaMalloc(&m->w_in, 64 * 80 * sizeof(float)));
+    CUDA_TRY(cudaMalloc(&m->w_front, sedb::kFrontWBytes));
     CUDA_TRY(cudaMalloc(&m->scale_in, 64 * sizeof(float)));
     CUDA_TRY(cudaMalloc(&m->shift_in, 64 * sizeof(float)));
     for (int i = 0; i < 8; ++i) {
@@ -512,6 +514,7 @@ int sedb_m5_create(sedb_ctx_t* ctx, int classes_num, sedb_m5_t** out) {
 int sedb_m5_destroy(sedb_m5_t* m) {
     if (!m) return 0;
     cudaFree(m->w_in);
+    cudaFree(m->w_front);
     cudaFree(m->scale_in);
     cudaFree(m->shift_in);
     for (auto& L : m->layers) free_layer_params(L);
@@ -530,7 +533,8 @@ int sedb_m5_load(sedb_m5_t* m, const float* const* t, int n_tensors, void* strea
     // pair 0: conv_block1 (k=79): conv.w conv.b bn.w bn.b bn.rm bn.rv
     CUDA_TRY(cudaMemcpyAsync(m->w_in, t[0], 64 * 79 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     sedb::bn_fold_kernel<<<1, 128, 0, st>>>(t[2], t[3], t[4], t[5], t[1], 1e-5f, 64, m->scale_in, m->shift_in);
-    g_launches.fetch_add(1);
+    sedb::pack_front_weight_kernel<<<(64 * 80 + 255) / 256, 256, 0, st>>>(m->w_in, m->w_front);
+    g_launches.fetch_add(2);
     for (int i = 0; i < 8; ++i) {
         const float* const* q = t + 6 * (i + 1);
         if (int rc = fold_and_pack(m->layers[i], q[0], q[1], q[2], q[3], q[4], q[5], st)) return rc;
@@ -566,10 +570,11 @@ int sedb_m5_forward(sedb_m5_t* m, const float* x_dev, long long n_frames, float*
     const int n = static_cast<int>(n_frames);
     {
         const PlaneGeom& g = plan.planes[0];
-        const int tiles = (g.W + sedb::kIn1dTile - 1) / sedb::kIn1dTile;
-        dim3 grid(tiles, n);
-        sedb::conv_in1d_kernel<<<grid, 256, sedb::kIn1dSmem, st>>>(x_dev, m->w_in, m->scale_in, m->shift_in, ws + g.offset,
-                                                                  kM5FrameLen, g.W, g.S);
+        const int L_conv = (kM5FrameLen + 2 * 39 - 79) / 4 + 1;                 // 7920
+        const long long items = static_cast<long long>(n) * ((L_conv + sedb::kFrontTilePos - 1) / sedb::kFrontTilePos);
+        const int grid = static_cast<int>(items < m->ctx->num_sms ? items : m->ctx->num_sms);
+        sedb::m5_front_kernel<<<grid, sedb::kFrontThreads, sedb::kFrontSmem, st>>>(
+            x_dev, m->w_front, m->scale_in, m->shift_in, ws + g.offset, n, kM5FrameLen, L_conv, g.W, g.S);
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
     }
