@@ -195,7 +195,7 @@ def run_reference(args):
                              "sample": f"{n_clips} clips/step, {workers} processes + {cores} torch threads"},
             "e2e": {"value": value, "unit": "audio-hours/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------- GPU arm
@@ -207,7 +207,6 @@ def run_ours(args):
     from sed_b200.dataset.spectogram import preprocess as P
     import refmodels
 
-    os.environ["NCCL_DEBUG"] = os.environ.get("SEDB_NCCL_DEBUG", "WARN")      # keep stdout to the one JSON line
     rank, local_rank, world = parallel.init_process_group("nccl" if int(os.environ.get("WORLD_SIZE", "1")) > 1 else None)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
@@ -319,10 +318,30 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(line), flush=True)
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Everything except the final JSON line goes to stderr: libraries (NCCL prints its version banner to fd 1) must
+    not pollute the one-line contract."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
+    _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
