@@ -138,14 +138,14 @@ inline std::vector<float> make_mel_matrix(int sr, int n_fft, int n_mels, double 
 //     mel_m = sum_k P_k w_m(k) = ar_m S1_m + br_m S0_m + af_m S1_{m+1} + bf_m S0_{m+1}
 // with the per-segment moments S0_s = sum P_k, S1_s = sum (k - kb_s) P_k over the bins kb_s <= k < kb_{s+1} of segment
 // s (segment m carries the rising edge of filter m, segment m+1 its falling edge).  Each bin is touched once instead
-// of once per overlapping filter and no weight table is read.  The bins are cut into pieces of <= 33 bins, one per
+// of once per overlapping filter and no weight table is read.  The bins are cut into pieces of <= 35 bins, one per
 // thread, so the accumulation needs no cross-lane reduction.  The lines are those of librosa.filters.mel (Slaney area
 // normalisation folded in), evaluated in fp32 by the kernels: they agree with the float32 matrix to ~1e-6 of the peak.
 struct MelTabEntry {
     int x, y, z, w;
 };
 constexpr int kMelSegments = 65;
-constexpr int kMelPieceLen = 33;      // bins per piece: consecutive lanes start on consecutive banks
+constexpr int kMelPieceLen = 35;      // bins per piece: odd, so consecutive lanes start on distinct banks; <= 512 pieces
 constexpr int kMelMaxPieces = 576;
 constexpr int kMelTabEntries = kMelMaxPieces / 2 + 80;      // int4 entries: 2 pieces each, then 65 segment ranges
 

@@ -139,7 +139,7 @@ __device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
 }
 
 // Mel filterbank over a power spectrum in shared memory, in moment form (host_tables.h): per segment between two mel
-// points S0 = sum P_k and S1 = sum (k - kb) P_k.  The bins are cut into pieces of <= 33 bins; thread `idx` accumulates
+// points S0 = sum P_k and S1 = sum (k - kb) P_k.  The bins are cut into pieces of <= 35 bins; thread `idx` accumulates
 // pieces idx, idx + nthreads, ... serially (two independent chains, no cross-lane reduction; consecutive lanes start on
 // consecutive banks) and writes the partial moments to the piece's own slot.  The slots of a segment are then added in
 // order by mel_finalize(), so the result does not depend on scheduling.  A block-level barrier goes in between.
