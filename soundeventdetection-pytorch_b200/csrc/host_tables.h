@@ -97,6 +97,25 @@ inline std::vector<float> make_hann_padded(int win, int n_fft) {
     return w;
 }
 
+// The same window in factored form for the kernel: w[128 m + n2] = sin^2(phi_m + psi_n2) with
+// phi_m = pi (128 m - lpad)/(win - 1), psi_n2 = pi n2/(win - 1) (0.5 - 0.5 cos(2x) = sin^2 x; relative accuracy is kept
+// at the window's ends).  Layout: 257 x {sin phi_m, cos phi_m}, then cos psi[128], then sin psi[128].
+inline std::vector<float> make_hann_factors(int win, int n_fft) {
+    const int lpad = (n_fft - win) / 2;
+    std::vector<float> t(2 * 257 + 256);
+    for (int m = 0; m <= 256; ++m) {
+        const double phi = kPi * static_cast<double>(128 * m - lpad) / (win - 1);
+        t[2 * m] = static_cast<float>(std::sin(phi));
+        t[2 * m + 1] = static_cast<float>(std::cos(phi));
+    }
+    for (int n = 0; n < 128; ++n) {
+        const double psi = kPi * static_cast<double>(n) / (win - 1);
+        t[2 * 257 + n] = static_cast<float>(std::cos(psi));
+        t[2 * 257 + 128 + n] = static_cast<float>(std::sin(psi));
+    }
+    return t;
+}
+
 // ---- librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax, htk=False, norm='slaney') --------------------
 inline double hz_to_mel(double f) {
     const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;

@@ -61,7 +61,9 @@ constexpr int kOffMelPart = kOffMelTab + kMelTabEntries * 16;   // partial momen
 constexpr int kOffMelCoef = kOffMelPart + 2 * kMelMaxPieces * 4;   // 64 x float4 line coefficients
 constexpr int kOffNorm = kOffMelCoef + 1024;               // mean[64], std[64] (when given)
 constexpr int kOffRed = kOffNorm + 512;                    // absmax reduction scratch (16 floats) + scale
-constexpr int kOffBars = kOffRed + 128;                    // mbarriers
+constexpr int kOffHannRow = kOffRed + 128;                 // window factors per row m: {sin, cos}(pi (128 m - 544)/31679), 257 x float2
+constexpr int kOffHannLane = kOffHannRow + 2064;           // window factors per column n2: cos[128] then sin[128] of pi n2/31679
+constexpr int kOffBars = kOffHannLane + 1024;              // mbarriers
 constexpr int kOffTmem = kOffBars + 256;                   // tmem base address
 constexpr int kSmemBytes = kOffTmem + 16;
 static_assert(kRingBytes >= (kBins + 3) * 4, "power spectrum must fit in the ring");
@@ -81,7 +83,7 @@ struct LogmelParams {
     int n_frames;             // T = 1 + n_samples / hop
     const uint8_t* a1;        // stage-1 constants, 8 chunks x 16 KB, canonical K-major, split hi/lo
     const uint8_t* b2;        // stage-2 constants, 4 x 16 KB
-    const float* hann;        // np.hanning(31680) centre-padded to 32768
+    const float* hann;        // factored np.hanning(31680): sin^2(pi i/31679), i = 128 m + n2 - 544 (host_tables.h: make_hann_factors)
     const float* mel_w;       // 64 x {ar, br, af, bf}: line coefficients of the moment form (host_tables.h)
     const int4* mel_tab;      // balanced piece table + per-segment slot ranges (host_tables.h)
     const float* norm;        // nullable: mean[64] then std[64]  (SpectogramDataset.transform, logMel mode)
@@ -219,6 +221,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
     float* coef_s = reinterpret_cast<float*>(smem + kOffMelCoef);
     float* norm_s = reinterpret_cast<float*>(smem + kOffNorm);
     float* red_s = reinterpret_cast<float*>(smem + kOffRed);
+    float2* hrow_s = reinterpret_cast<float2*>(smem + kOffHannRow);
+    float* hlane_s = reinterpret_cast<float*>(smem + kOffHannLane);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
@@ -251,6 +255,10 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         float s, c;
         sincospif(static_cast<float>(i) * (1.0f / 128.0f), &s, &c);      // exp(-2 pi i j/256) = (c, -s)
         cs_s[i] = make_float2(c, -s);
+    }
+    for (int i = tid; i < 2 * 257 + 256; i += kThreads) {
+        const float v = prm.hann[i];
+        if (i < 2 * 257) reinterpret_cast<float*>(hrow_s)[i] = v; else hlane_s[i - 2 * 257] = v;
     }
     for (int i = tid; i < kMelTabEntries; i += kThreads) mel_tab_s[i] = prm.mel_tab[i];
     for (int i = tid; i < 4 * kMel; i += kThreads) coef_s[i] = prm.mel_w[i];
@@ -430,7 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 xb[c] = load4(128 * mb + 4 * lane);
             }
             // ---------------------------------------------------------------- per-frame block scale (fp16 halves)
-            float scale = 1.0f, inv_scale = 1.0f;
+            float scale = 1.0f, inv_scale = 1.0f, sqrt_scale = 1.0f;
 #if SEDB_SPLIT_FP16
             {
                 float mx = 0.f;
@@ -446,34 +454,38 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 mx = red_s[lane & 15];
 #pragma unroll
                 for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                // scale = 2^(5 - floor(log2 max)): |x| scale < 64, so no intermediate can exceed 2^15 < 65504
+                // scale = 2^e, e = 5 - floor(log2 max) rounded down to even: |x| scale < 64, so no intermediate can
+                // exceed 2^15 < 65504; sqrt(scale) rides on the window factors
                 int e = 0;
                 if (mx > 0.f && mx < 3.0e38f) e = 5 - (static_cast<int>((__float_as_uint(mx) >> 23) & 0xff) - 127);
-                e = max(-56, min(60, e));
+                e = max(-56, min(60, e)) & ~1;
                 scale = __uint_as_float(static_cast<uint32_t>(127 + e) << 23);
                 inv_scale = __uint_as_float(static_cast<uint32_t>(127 - e) << 23);
+                sqrt_scale = __uint_as_float(static_cast<uint32_t>(127 + e / 2) << 23);
             }
 #endif
             SEDB_PROF(0);   // frame load (+ block scale)
             // ---------------------------------------------------------------- stage 1: window, fold, split
             float alt[4] = {0.f, 0.f, 0.f, 0.f};
-            auto hann4 = [&](int row) { return __ldg(reinterpret_cast<const float4*>(prm.hann + 128 * row + 4 * lane)); };
-            float4 wa_n = hann4(r), wb_n = hann4(r == 0 ? 128 : 256 - r);
+            // window w = sin^2(phi_m + phi_n2) from the factor tables (no per-frame window traffic from L2)
+            const float4 hc = *reinterpret_cast<const float4*>(hlane_s + 4 * lane);
+            const float4 hs = *reinterpret_cast<const float4*>(hlane_s + 128 + 4 * lane);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const int g = it * 8 + c;
                 const int s = g % kNumSlots;
                 const int u = g / kNumSlots;
                 const int m = 16 * c + r;
-                const float4 wa = wa_n, wb = wb_n;
-                if (c + 1 < 8) {                                  // window values of the next chunk (L2) in flight
-                    wa_n = hann4(m + 16);
-                    wb_n = hann4(256 - (m + 16));
-                }
-                const float a0 = xa[c].x * wa.x * scale, a1 = xa[c].y * wa.y * scale;
-                const float a2 = xa[c].z * wa.z * scale, a3 = xa[c].w * wa.w * scale;
-                const float b0 = xb[c].x * wb.x * scale, b1 = xb[c].y * wb.y * scale;
-                const float b2 = xb[c].z * wb.z * scale, b3 = xb[c].w * wb.w * scale;
+                float2 ra = hrow_s[m], rb = hrow_s[m == 0 ? 128 : 256 - m];
+                ra.x *= sqrt_scale; ra.y *= sqrt_scale; rb.x *= sqrt_scale; rb.y *= sqrt_scale;
+                auto win = [](float x, float2 rw, float cn, float sn) {
+                    const float t = fmaf(rw.y, sn, rw.x * cn);      // sqrt(scale) sin(phi_m + phi_n2)
+                    return x * (t * t);
+                };
+                const float a0 = win(xa[c].x, ra, hc.x, hs.x), a1 = win(xa[c].y, ra, hc.y, hs.y);
+                const float a2 = win(xa[c].z, ra, hc.z, hs.z), a3 = win(xa[c].w, ra, hc.w, hs.w);
+                const float b0 = win(xb[c].x, rb, hc.x, hs.x), b1 = win(xb[c].y, rb, hc.y, hs.y);
+                const float b2 = win(xb[c].z, rb, hc.z, hs.z), b3 = win(xb[c].w, rb, hc.w, hs.w);
                 float u4[4], v4[4];
                 if (m == 0) {                                   // warp-uniform: U[0] = X[0], V[0] = 0, keep X[128]
                     u4[0] = a0; u4[1] = a1; u4[2] = a2; u4[3] = a3;

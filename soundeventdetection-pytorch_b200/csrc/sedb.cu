@@ -46,7 +46,7 @@ struct sedb_ctx {
     int num_sms = 0;
     uint8_t* a1 = nullptr;        // stage-1 DFT constants
     uint8_t* b2 = nullptr;        // stage-2 DFT constants
-    float* hann = nullptr;        // padded Hann window
+    float* hann = nullptr;        // factored Hann window tables (make_hann_factors)
     float* mel_w = nullptr;       // per-filter line coefficients {a_r, b_r, a_f, b_f}
     int4* mel_tab = nullptr;      // per-filter band table
     // host-buffer pipeline state (sedb_logmel_host_f32 / sedb_sed_host_f32)
@@ -116,7 +116,7 @@ int sedb_create(sedb_ctx_t** out_ctx) {
         return fail("sedb_create: mel work table does not fit");
     CUDA_TRY(cudaMalloc(&c->a1, a1.size()));
     CUDA_TRY(cudaMalloc(&c->b2, b2.size()));
-    std::vector<float> hann = sedb_host::make_hann_padded(SEDB_FRAME_SIZE, SEDB_NFFT);
+    std::vector<float> hann = sedb_host::make_hann_factors(SEDB_FRAME_SIZE, SEDB_NFFT);
     CUDA_TRY(cudaMalloc(&c->hann, hann.size() * sizeof(float)));
     CUDA_TRY(cudaMemcpy(c->hann, hann.data(), hann.size() * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc(&c->mel_w, wts.size() * sizeof(float)));
