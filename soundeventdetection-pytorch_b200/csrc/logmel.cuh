@@ -73,7 +73,9 @@ constexpr int kWorkerWarps = 16;
 constexpr int kWorkerThreads = kWorkerWarps * 32;
 constexpr int kMmaWarp = 16;
 constexpr int kCopyWarp = 17;
-constexpr int kThreads = 576;
+constexpr int kThreads = 640;                // 16 workers + MMA + copy + 2 idle warps (register allocation is per 4 warps anyway)
+constexpr int kWorkerRegs = 112;             // setmaxnreg: the service warp group gives its registers to the workers
+constexpr int kServiceRegs = 24;
 
 struct LogmelParams {
     const float* wave;        // [B, wave_stride] fp32
@@ -275,7 +277,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                            : 0;
 
     // ======================================================================== bulk-copy producer warp
-    if (warp == kCopyWarp) {
+    // register re-allocation between warp groups: 4 service warps x 32 regs + 16 worker warps x 112 regs = the 96 x 640
+    // registers the CTA was launched with
+    // (issued at the top of each role's own branch: ptxas allocates per region between setmaxnreg and the join)
+    if (warp >= kWorkerWarps + 2) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kServiceRegs));
+    } else if (warp == kCopyWarp) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kServiceRegs));
         if (elect_one()) {
             mbar_arrive_expect_tx(b2_full, kB2Bytes);
             for (int a = 0; a < 4; ++a)
@@ -313,6 +321,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
     }
     // ======================================================================== MMA issuer warp
     else if (warp == kMmaWarp) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kServiceRegs));
         // The whole warp stays converged and one elected lane issues: every operand is then warp-uniform (the
         // 512-column allocation starts at TMEM address 0) and each MMA costs a handful of uniform-datapath
         // instructions.  A lane-divergent `if (lane == 0)` region makes ptxas wrap every tcgen05.mma in a vote loop.
@@ -380,7 +389,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         }
     }
     // ======================================================================== 16 worker warps
-    else {
+    else if (warp < kWorkerWarps) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWorkerRegs));
         const int q = warp & 3;                 // TMEM lane quarter
         const int sub = warp >> 2;              // which 4 of a chunk's 16 columns (stage-2 operand), which 16 of 64 (output)
         const int k1 = q * 32 + lane;           // this thread's stage-1 output row / stage-2 A row
