@@ -63,7 +63,8 @@ constexpr int kOffNorm = kOffMelCoef + 1024;               // mean[64], std[64] 
 constexpr int kOffRed = kOffNorm + 512;                    // absmax reduction scratch (16 floats) + scale
 constexpr int kOffHannRow = kOffRed + 128;                 // window factors per row m: {sin, cos}(pi (128 m - 544)/31679), 257 x float2
 constexpr int kOffHannLane = kOffHannRow + 2064;           // window factors per column n2: cos[128] then sin[128] of pi n2/31679
-constexpr int kOffBars = kOffHannLane + 1024;              // mbarriers
+constexpr int kOffE1Tw = kOffHannLane + 1024;              // exp(-2 pi i n/128), n < 64: re[64] then im[64]
+constexpr int kOffBars = kOffE1Tw + 512;                   // mbarriers
 constexpr int kOffTmem = kOffBars + 256;                   // tmem base address
 constexpr int kSmemBytes = kOffTmem + 16;
 static_assert(kRingBytes >= (kBins + 3) * 4, "power spectrum must fit in the ring");
@@ -127,6 +128,10 @@ __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
                  : "memory");
 #pragma unroll
     for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void split4(const float2* x, uint2& hi, uint2& lo) {
+    split_pack2(x[0], hi.x, lo.x);
+    split_pack2(x[1], hi.y, lo.y);
 }
 __device__ __forceinline__ void split4(const float* x, uint2& hi, uint2& lo) {
     split_pack2(x[0], x[1], hi.x, lo.x);
@@ -225,6 +230,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
     float* red_s = reinterpret_cast<float*>(smem + kOffRed);
     float2* hrow_s = reinterpret_cast<float2*>(smem + kOffHannRow);
     float* hlane_s = reinterpret_cast<float*>(smem + kOffHannLane);
+    float* e1tw_s = reinterpret_cast<float*>(smem + kOffE1Tw);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
     uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(smem + kOffTmem);
 
@@ -257,6 +263,10 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         float s, c;
         sincospif(static_cast<float>(i) * (1.0f / 128.0f), &s, &c);      // exp(-2 pi i j/256) = (c, -s)
         cs_s[i] = make_float2(c, -s);
+        if ((i & 1) == 0 && i < 128) {
+            e1tw_s[i >> 1] = c;
+            e1tw_s[64 + (i >> 1)] = -s;
+        }
     }
     for (int i = tid; i < 2 * 257 + 256; i += kThreads) {
         const float v = prm.hann[i];
@@ -398,9 +408,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         const float sgn_k1 = (k1 & 1) ? -1.f : 1.f;
 
         // per-thread twiddle constants, W = exp(-2 pi i k1/32768): W^j (j=1..3), anchors W^(16 c + 4 sub), W^64
-        float2 wj[4], anc[4], w64;
+        // (the j-twiddles are kept as pairs (j, j+1) for packed arithmetic; W^0 = 1)
+        float2 wre01, wim01, wre23, wim23, anc[4], w64;
         {
             float s, c;
+            float2 wj[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 sincospif(static_cast<float>(k1 * j) * (1.0f / 16384.0f), &s, &c);
@@ -408,6 +420,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 sincospif(static_cast<float>(k1 * (16 * j + 4 * sub)) * (1.0f / 16384.0f), &s, &c);
                 anc[j] = make_float2(c, -s);
             }
+            wre01 = f2(1.f, wj[1].x); wim01 = f2(0.f, wj[1].y);
+            wre23 = f2(wj[2].x, wj[3].x); wim23 = f2(wj[2].y, wj[3].y);
             sincospif(static_cast<float>(k1 * 64) * (1.0f / 16384.0f), &s, &c);
             w64 = make_float2(c, -s);
         }
@@ -476,10 +490,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
 #endif
             SEDB_PROF(0);   // frame load (+ block scale)
             // ---------------------------------------------------------------- stage 1: window, fold, split
-            float alt[4] = {0.f, 0.f, 0.f, 0.f};
-            // window w = sin^2(phi_m + phi_n2) from the factor tables (no per-frame window traffic from L2)
+            float2 alt01 = f2s(0.f), alt23 = f2s(0.f);
+            // window w = sin^2(phi_m + phi_n2) from the factor tables (no per-frame window traffic from L2); packed fp32
+            // arithmetic throughout (two samples per instruction)
             const float4 hc = *reinterpret_cast<const float4*>(hlane_s + 4 * lane);
             const float4 hs = *reinterpret_cast<const float4*>(hlane_s + 128 + 4 * lane);
+            const float2 hc01 = f2(hc.x, hc.y), hc23 = f2(hc.z, hc.w), hs01 = f2(hs.x, hs.y), hs23 = f2(hs.z, hs.w);
 #pragma unroll
             for (int c = 0; c < 8; ++c) {
                 const int g = it * 8 + c;
@@ -488,30 +504,30 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 const int m = 16 * c + r;
                 float2 ra = hrow_s[m], rb = hrow_s[m == 0 ? 128 : 256 - m];
                 ra.x *= sqrt_scale; ra.y *= sqrt_scale; rb.x *= sqrt_scale; rb.y *= sqrt_scale;
-                auto win = [](float x, float2 rw, float cn, float sn) {
-                    const float t = fmaf(rw.y, sn, rw.x * cn);      // sqrt(scale) sin(phi_m + phi_n2)
-                    return x * (t * t);
+                auto win2 = [](float2 x, float2 rw, float2 cn, float2 sn) {
+                    const float2 t = f2fma(f2s(rw.y), sn, f2mul(f2s(rw.x), cn));   // sqrt(scale) sin(phi_m + phi_n2)
+                    return f2mul(x, f2mul(t, t));
                 };
-                const float a0 = win(xa[c].x, ra, hc.x, hs.x), a1 = win(xa[c].y, ra, hc.y, hs.y);
-                const float a2 = win(xa[c].z, ra, hc.z, hs.z), a3 = win(xa[c].w, ra, hc.w, hs.w);
-                const float b0 = win(xb[c].x, rb, hc.x, hs.x), b1 = win(xb[c].y, rb, hc.y, hs.y);
-                const float b2 = win(xb[c].z, rb, hc.z, hs.z), b3 = win(xb[c].w, rb, hc.w, hs.w);
-                float u4[4], v4[4];
+                const float2 a01 = win2(f2(xa[c].x, xa[c].y), ra, hc01, hs01);
+                const float2 a23 = win2(f2(xa[c].z, xa[c].w), ra, hc23, hs23);
+                const float2 b01 = win2(f2(xb[c].x, xb[c].y), rb, hc01, hs01);
+                const float2 b23 = win2(f2(xb[c].z, xb[c].w), rb, hc23, hs23);
+                float2 u01, u23, v01, v23;
                 if (m == 0) {                                   // warp-uniform: U[0] = X[0], V[0] = 0, keep X[128]
-                    u4[0] = a0; u4[1] = a1; u4[2] = a2; u4[3] = a3;
-                    v4[0] = v4[1] = v4[2] = v4[3] = 0.f;
-                    *reinterpret_cast<float4*>(x128_s + 4 * lane) = make_float4(b0, b1, b2, b3);
+                    u01 = a01; u23 = a23;
+                    v01 = v23 = f2s(0.f);
+                    *reinterpret_cast<float4*>(x128_s + 4 * lane) = make_float4(b01.x, b01.y, b23.x, b23.y);
                 } else {
-                    u4[0] = a0 + b0; u4[1] = a1 + b1; u4[2] = a2 + b2; u4[3] = a3 + b3;
-                    v4[0] = a0 - b0; v4[1] = a1 - b1; v4[2] = a2 - b2; v4[3] = a3 - b3;
+                    u01 = f2add(a01, b01); u23 = f2add(a23, b23);
+                    v01 = f2sub(a01, b01); v23 = f2sub(a23, b23);
                 }
-#pragma unroll
-                for (int e = 0; e < 4; ++e) alt[e] += u4[e];
+                alt01 = f2add(alt01, u01);
+                alt23 = f2add(alt23, u23);
                 uint32_t uh[2], ul[2], vh[2], vl[2];
-                split_pack2(u4[0], u4[1], uh[0], ul[0]);
-                split_pack2(u4[2], u4[3], uh[1], ul[1]);
-                split_pack2(v4[0], v4[1], vh[0], vl[0]);
-                split_pack2(v4[2], v4[3], vh[1], vl[1]);
+                split_pack2(u01, uh[0], ul[0]);
+                split_pack2(u23, uh[1], ul[1]);
+                split_pack2(v01, vh[0], vl[0]);
+                split_pack2(v23, vh[1], vl[1]);
                 mbar_wait(&empty1[s], (u & 1) ^ 1);
                 uint8_t* dst = ring + s * kSlotBytes + b1_off;
                 *reinterpret_cast<uint2*>(dst + 0 * kB1ArrBytes) = make_uint2(uh[0], uh[1]);
@@ -524,7 +540,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
             }
             // alternating row sums for k1 = 128: row r of every chunk has parity r
             *reinterpret_cast<float4*>(alt_s + r * 128 + 4 * lane) =
-                make_float4(alt_sign * alt[0], alt_sign * alt[1], alt_sign * alt[2], alt_sign * alt[3]);
+                make_float4(alt_sign * alt01.x, alt_sign * alt01.y, alt_sign * alt23.x, alt_sign * alt23.y);
 
             SEDB_PROF(1);   // fold / split / store
             // ---------------------------------------------------------------- twiddle, radix-2, stage-2 A operand
@@ -548,20 +564,31 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 tmem_ld4(tlane + 128 + n0, s0);
                 tmem_ld4(tlane + 192 + n0, s1);
                 tmem_ld_wait();
-                float er[4], ei[4], orr[4], oi[4];
+                // packed fp32: pairs of columns (jj, jj + 1)
+                const float4 xlo = *reinterpret_cast<const float4*>(x128_s + n0);
+                const float4 xhi = *reinterpret_cast<const float4*>(x128_s + 64 + n0);
+                const float4 cre = *reinterpret_cast<const float4*>(e1tw_s + n0);
+                const float4 cim = *reinterpret_cast<const float4*>(e1tw_s + 64 + n0);
+                const float2 ancx = f2s(anc[c].x), ancy = f2s(anc[c].y), w64x = f2s(w64.x), w64y = f2s(w64.y);
+                float2 er[2], ei[2], orr[2], oi[2];
 #pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const float2 tw0 = (jj == 0) ? anc[c] : cmul(anc[c], wj[jj]);
-                    const float2 tw1 = cmul(tw0, w64);
-                    const float yr0 = fmaf(sgn_k1, x128_s[n0 + jj], c0[jj]);
-                    const float yr1 = fmaf(sgn_k1, x128_s[64 + n0 + jj], c1[jj]);
-                    const float2 z0 = cmul(make_float2(yr0, s0[jj]), tw0);
-                    const float2 z1 = cmul(make_float2(yr1, s1[jj]), tw1);
-                    er[jj] = z0.x + z1.x;
-                    ei[jj] = z0.y + z1.y;
-                    const float2 o = cmul(make_float2(z0.x - z1.x, z0.y - z1.y), cs_s[2 * (n0 + jj)]);
-                    orr[jj] = o.x;
-                    oi[jj] = o.y;
+                for (int h = 0; h < 2; ++h) {
+                    const float2 wre = h ? wre23 : wre01, wim = h ? wim23 : wim01;
+                    const float2 t0r = f2fma(f2neg(ancy), wim, f2mul(ancx, wre));      // tw0 = anc * W^j
+                    const float2 t0i = f2fma(ancy, wre, f2mul(ancx, wim));
+                    const float2 t1r = f2fma(f2neg(w64y), t0i, f2mul(w64x, t0r));      // tw1 = tw0 * W^64
+                    const float2 t1i = f2fma(w64x, t0i, f2mul(w64y, t0r));
+                    const float2 y0 = f2fma(f2s(sgn_k1), h ? f2(xlo.z, xlo.w) : f2(xlo.x, xlo.y), f2(c0[2 * h], c0[2 * h + 1]));
+                    const float2 y1 = f2fma(f2s(sgn_k1), h ? f2(xhi.z, xhi.w) : f2(xhi.x, xhi.y), f2(c1[2 * h], c1[2 * h + 1]));
+                    const float2 v0 = f2(s0[2 * h], s0[2 * h + 1]), v1 = f2(s1[2 * h], s1[2 * h + 1]);
+                    const float2 z0r = f2fma(f2neg(v0), t0i, f2mul(y0, t0r)), z0i = f2fma(v0, t0r, f2mul(y0, t0i));
+                    const float2 z1r = f2fma(f2neg(v1), t1i, f2mul(y1, t1r)), z1i = f2fma(v1, t1r, f2mul(y1, t1i));
+                    er[h] = f2add(z0r, z1r);
+                    ei[h] = f2add(z0i, z1i);
+                    const float2 dr = f2sub(z0r, z1r), di = f2sub(z0i, z1i);
+                    const float2 cr = h ? f2(cre.z, cre.w) : f2(cre.x, cre.y), ci = h ? f2(cim.z, cim.w) : f2(cim.x, cim.y);
+                    orr[h] = f2fma(f2neg(di), ci, f2mul(dr, cr));
+                    oi[h] = f2fma(di, cr, f2mul(dr, ci));
                 }
                 // K-major A operand: row k1, K index 4 sub + jj -> K-group sub/2, byte (sub&1)*8 inside the 16-B row
                 uint8_t* d = ring + c * kSlotBytes + (sub >> 1) * 2048 + k1 * 16 + (sub & 1) * 8;
@@ -625,6 +652,16 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                     tmem_ld8(tlane + 256 + 128 * par + j0, re);
                     tmem_ld8(tlane + 256 + 128 * par + 64 + j0, im);
                     tmem_ld_wait();
+                    float pw[8];
+                    if (MODE == 0) {
+#pragma unroll
+                        for (int i = 0; i < 8; i += 2) {
+                            const float2 q = f2fma(f2(re[i], re[i + 1]), f2(re[i], re[i + 1]),
+                                                   f2mul(f2(im[i], im[i + 1]), f2(im[i], im[i + 1])));
+                            pw[i] = q.x;
+                            pw[i + 1] = q.y;
+                        }
+                    }
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int k = k1 + 256 * (2 * (j0 + i) + par);
@@ -634,7 +671,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                         else if (k1 >= 1) { bin = kNfft - k; sgn = -1.f; }        // Hermitian mirror (conjugate)
                         else bin = (k == kNfft / 2) ? k : -1;
                         if (bin >= 0) {
-                            if (MODE == 0) p_s[bin] = re[i] * re[i] + im[i] * im[i];
+                            if (MODE == 0) p_s[bin] = pw[i];
                             else spec_row[bin] = make_float2(re[i] * inv_scale, sgn * im[i] * inv_scale);
                         }
                     }

@@ -217,4 +217,28 @@ __device__ __forceinline__ void split_pack2(float x0, float x1, uint32_t& hi, ui
 #endif
 }
 
+// ---- packed fp32 arithmetic (sm_100 FFMA2 / FMUL2 / FADD2: two fp32 results per issue slot) ---------------------
+__device__ __forceinline__ float2 f2(float a, float b) { return make_float2(a, b); }
+__device__ __forceinline__ float2 f2s(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 f2neg(float2 a) { return make_float2(-a.x, -a.y); }   // folds into an operand modifier
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+
+// split_pack2 on a register pair (the lo subtraction is one packed instruction)
+__device__ __forceinline__ void split_pack2(float2 x, uint32_t& hi, uint32_t& lo) {
+#if SEDB_SPLIT_FP16
+    const float2 h = make_float2(__uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u),
+                                 __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u));
+    const float2 l = f2sub(x, h);
+    const __half2 hh = __floats2half2_rn(h.x, h.y);
+    const __half2 ll = __floats2half2_rn(l.x, l.y);
+    hi = *reinterpret_cast<const uint32_t*>(&hh);
+    lo = *reinterpret_cast<const uint32_t*>(&ll);
+#else
+    split_pack2(x.x, x.y, hi, lo);
+#endif
+}
+
 }  // namespace sedb
