@@ -71,8 +71,12 @@ inline std::vector<uint8_t> make_stage2_constants(bool fp16) {
     std::vector<uint8_t> buf(4 * 16384);
     for (int col = 0; col < 128; ++col)
         for (int k = 0; k < 64; ++k) {
+            // K position k of chunk k/16 holds column n = 16 (k/16) + 2 s + (jj & 1) + 8 (jj >> 1), s = (k%16)/4,
+            // jj = k%4: the order in which the worker threads lay their columns into the TMEM A operand (logmel.cuh)
+            const int p16 = k % 16, sq = p16 / 4, jj = p16 % 4;
+            const int n = 16 * (k / 16) + 2 * sq + (jj & 1) + 8 * (jj >> 1);
             const int j = col & 63;
-            const double ang = 2.0 * kPi * static_cast<double>((k * j) % 64) / 64.0;
+            const double ang = 2.0 * kPi * static_cast<double>((n * j) % 64) / 64.0;
             const double cv = std::cos(ang), sv = std::sin(ang);
             const double bre = (col < 64) ? cv : -sv;
             const double bim = (col < 64) ? sv : cv;

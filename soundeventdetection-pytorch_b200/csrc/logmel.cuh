@@ -120,6 +120,12 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ void tmem_ld2(uint32_t taddr, float* v) {
+    uint32_t r[2];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr) : "memory");
+    v[0] = __uint_as_float(r[0]);
+    v[1] = __uint_as_float(r[1]);
+}
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
     uint32_t r[4];
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
@@ -343,9 +349,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         // descriptors for slot 0 / K-chunk 0; other slots and chunks add to the start-address field (16-byte units)
         const uint64_t dA1 = make_smem_desc(ring_a, 2048, 128);                         // cH; cL, sH, sL follow
         const uint64_t dB1 = make_smem_desc(ring_a + kA1ChunkBytes, kB1Lbo, kB1Sbo);     // uH; uL, vH, vL follow
-        const uint64_t dA2 = make_smem_desc(ring_a, 2048, 128);                         // stage-2 operand arrays
         const uint64_t dB2 = make_smem_desc(b2_a, 2048, 128);                           // reH; reL, imH, imL follow
-        constexpr uint32_t kA1Step = kA1ArrBytes >> 4, kB1Step = kB1ArrBytes >> 4, kA2Step = kA2ArrBytes >> 4;
+        constexpr uint32_t kA1Step = kA1ArrBytes >> 4, kB1Step = kB1ArrBytes >> 4;
         constexpr uint32_t kB2Step = kB2ArrBytes >> 4, kSlotStep = kSlotBytes >> 4;
         mbar_wait(b2_full, 0);
         for (int it = 0; it < n_iter; ++it) {
@@ -371,26 +376,27 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 }
                 __syncwarp();
             }
-            // ---------------- stage 2: 4 K-chunks of 16 columns (n), even and odd outputs
+            // ---------------- stage 2: 4 K-chunks of 16 columns (n), even and odd outputs; A operand from TMEM
 #pragma unroll 1
             for (int j = 0; j < 4; ++j) {
                 mbar_wait(&full2[j], it & 1);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint64_t a = dA2 + j * kSlotStep;            // real hi, real lo, imag hi, imag lo of E then O
+                    // E: re hi/lo at columns 16 j / 16 j + 8, im hi/lo at 64 + ...; O: 128 + ..., 192 + ...
+                    const uint32_t a = 16 * j;
                     const uint64_t bre = dB2 + j * ((2 * 2048) >> 4);  // 16 n = 2 K-groups
                     const uint64_t bim = bre + 2 * kB2Step;
                     const uint32_t acc = (j > 0) ? 1u : 0u;
 #pragma unroll
                     for (int par = 0; par < 2; ++par) {
                         const uint32_t d = 256 + 128 * par;
-                        const uint64_t ap = a + 4 * par * kA2Step;
-                        umma_f16(d, ap, bre, idesc2, acc);
-                        umma_f16(d, ap + kA2Step, bre, idesc2, 1u);
-                        umma_f16(d, ap, bre + kB2Step, idesc2, 1u);
-                        umma_f16(d, ap + 2 * kA2Step, bim, idesc2, 1u);
-                        umma_f16(d, ap + 3 * kA2Step, bim, idesc2, 1u);
-                        umma_f16(d, ap + 2 * kA2Step, bim + kB2Step, idesc2, 1u);
+                        const uint32_t ap = a + 128 * par;
+                        umma_f16_ts(d, ap, bre, idesc2, acc);                  // reH breH
+                        umma_f16_ts(d, ap + 8, bre, idesc2, 1u);               // reL breH
+                        umma_f16_ts(d, ap, bre + kB2Step, idesc2, 1u);         // reH breL
+                        umma_f16_ts(d, ap + 64, bim, idesc2, 1u);              // imH bimH
+                        umma_f16_ts(d, ap + 64 + 8, bim, idesc2, 1u);          // imL bimH
+                        umma_f16_ts(d, ap + 64, bim + kB2Step, idesc2, 1u);    // imH bimL
                     }
                     if (j == 3) umma_commit(d2_full);
                 }
@@ -415,9 +421,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
             float2 wj[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                sincospif(static_cast<float>(k1 * j) * (1.0f / 16384.0f), &s, &c);
+                sincospif(static_cast<float>(k1 * ((j & 1) + 8 * (j >> 1))) * (1.0f / 16384.0f), &s, &c);
                 wj[j] = make_float2(c, -s);
-                sincospif(static_cast<float>(k1 * (16 * j + 4 * sub)) * (1.0f / 16384.0f), &s, &c);
+                sincospif(static_cast<float>(k1 * (16 * j + 2 * sub)) * (1.0f / 16384.0f), &s, &c);
                 anc[j] = make_float2(c, -s);
             }
             wre01 = f2(1.f, wj[1].x); wim01 = f2(0.f, wj[1].y);
@@ -556,56 +562,63 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
             }
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
-                // chunk c = columns n in [16 c, 16 c + 16) (and n + 64); this warp owns n0 .. n0 + 3
-                const int n0 = 16 * c + 4 * sub;
+                // chunk c = columns n in [16 c, 16 c + 16) (and n + 64); this thread owns n = na + {0, 1, 8, 9}.
+                // The stage-2 A operand goes back into the very TMEM columns the thread has just read (two K elements
+                // per 32-bit column): array a of chunk c lives at column 64 (a >> 1) + 16 c + 8 (a & 1), this thread's
+                // K indices 4 sub .. 4 sub + 3 are the columns + 2 sub, + 2 sub + 1.  No shared memory, no proxy fence.
+                const int na = 16 * c + 2 * sub;
                 float c0[4], c1[4], s0[4], s1[4];
-                tmem_ld4(tlane + n0, c0);
-                tmem_ld4(tlane + 64 + n0, c1);
-                tmem_ld4(tlane + 128 + n0, s0);
-                tmem_ld4(tlane + 192 + n0, s1);
+                tmem_ld2(tlane + na, c0);
+                tmem_ld2(tlane + na + 8, c0 + 2);
+                tmem_ld2(tlane + 64 + na, c1);
+                tmem_ld2(tlane + 64 + na + 8, c1 + 2);
+                tmem_ld2(tlane + 128 + na, s0);
+                tmem_ld2(tlane + 128 + na + 8, s0 + 2);
+                tmem_ld2(tlane + 192 + na, s1);
+                tmem_ld2(tlane + 192 + na + 8, s1 + 2);
                 tmem_ld_wait();
-                // packed fp32: pairs of columns (jj, jj + 1)
-                const float4 xlo = *reinterpret_cast<const float4*>(x128_s + n0);
-                const float4 xhi = *reinterpret_cast<const float4*>(x128_s + 64 + n0);
-                const float4 cre = *reinterpret_cast<const float4*>(e1tw_s + n0);
-                const float4 cim = *reinterpret_cast<const float4*>(e1tw_s + 64 + n0);
-                const float2 ancx = f2s(anc[c].x), ancy = f2s(anc[c].y), w64x = f2s(w64.x), w64y = f2s(w64.y);
+                // packed fp32: pairs of columns (na, na + 1) and (na + 8, na + 9)
+                const float2 an = (c == 0) ? anc[0] : (c == 1) ? anc[1] : (c == 2) ? anc[2] : anc[3];   // registers, no local array
+                const float2 ancx = f2s(an.x), ancy = f2s(an.y), w64x = f2s(w64.x), w64y = f2s(w64.y);
                 float2 er[2], ei[2], orr[2], oi[2];
 #pragma unroll
                 for (int h = 0; h < 2; ++h) {
                     const float2 wre = h ? wre23 : wre01, wim = h ? wim23 : wim01;
+                    const float2 xlo = *reinterpret_cast<const float2*>(x128_s + na + 8 * h);
+                    const float2 xhi = *reinterpret_cast<const float2*>(x128_s + 64 + na + 8 * h);
+                    const float2 cr = *reinterpret_cast<const float2*>(e1tw_s + na + 8 * h);
+                    const float2 ci = *reinterpret_cast<const float2*>(e1tw_s + 64 + na + 8 * h);
                     const float2 t0r = f2fma(f2neg(ancy), wim, f2mul(ancx, wre));      // tw0 = anc * W^j
                     const float2 t0i = f2fma(ancy, wre, f2mul(ancx, wim));
                     const float2 t1r = f2fma(f2neg(w64y), t0i, f2mul(w64x, t0r));      // tw1 = tw0 * W^64
                     const float2 t1i = f2fma(w64x, t0i, f2mul(w64y, t0r));
-                    const float2 y0 = f2fma(f2s(sgn_k1), h ? f2(xlo.z, xlo.w) : f2(xlo.x, xlo.y), f2(c0[2 * h], c0[2 * h + 1]));
-                    const float2 y1 = f2fma(f2s(sgn_k1), h ? f2(xhi.z, xhi.w) : f2(xhi.x, xhi.y), f2(c1[2 * h], c1[2 * h + 1]));
+                    const float2 y0 = f2fma(f2s(sgn_k1), xlo, f2(c0[2 * h], c0[2 * h + 1]));
+                    const float2 y1 = f2fma(f2s(sgn_k1), xhi, f2(c1[2 * h], c1[2 * h + 1]));
                     const float2 v0 = f2(s0[2 * h], s0[2 * h + 1]), v1 = f2(s1[2 * h], s1[2 * h + 1]);
                     const float2 z0r = f2fma(f2neg(v0), t0i, f2mul(y0, t0r)), z0i = f2fma(v0, t0r, f2mul(y0, t0i));
                     const float2 z1r = f2fma(f2neg(v1), t1i, f2mul(y1, t1r)), z1i = f2fma(v1, t1r, f2mul(y1, t1i));
                     er[h] = f2add(z0r, z1r);
                     ei[h] = f2add(z0i, z1i);
                     const float2 dr = f2sub(z0r, z1r), di = f2sub(z0i, z1i);
-                    const float2 cr = h ? f2(cre.z, cre.w) : f2(cre.x, cre.y), ci = h ? f2(cim.z, cim.w) : f2(cim.x, cim.y);
                     orr[h] = f2fma(f2neg(di), ci, f2mul(dr, cr));
                     oi[h] = f2fma(di, cr, f2mul(dr, ci));
                 }
-                // K-major A operand: row k1, K index 4 sub + jj -> K-group sub/2, byte (sub&1)*8 inside the 16-B row
-                uint8_t* d = ring + c * kSlotBytes + (sub >> 1) * 2048 + k1 * 16 + (sub & 1) * 8;
+                const uint32_t ta = tlane + 16 * c + 2 * sub;
                 uint2 h, l;
                 split4(er, h, l);
-                *reinterpret_cast<uint2*>(d + 0 * kA2ArrBytes) = h;
-                *reinterpret_cast<uint2*>(d + 1 * kA2ArrBytes) = l;
+                tmem_st2(ta, h.x, h.y);
+                tmem_st2(ta + 8, l.x, l.y);
                 split4(ei, h, l);
-                *reinterpret_cast<uint2*>(d + 2 * kA2ArrBytes) = h;
-                *reinterpret_cast<uint2*>(d + 3 * kA2ArrBytes) = l;
+                tmem_st2(ta + 64, h.x, h.y);
+                tmem_st2(ta + 64 + 8, l.x, l.y);
                 split4(orr, h, l);
-                *reinterpret_cast<uint2*>(d + 4 * kA2ArrBytes) = h;
-                *reinterpret_cast<uint2*>(d + 5 * kA2ArrBytes) = l;
+                tmem_st2(ta + 128, h.x, h.y);
+                tmem_st2(ta + 128 + 8, l.x, l.y);
                 split4(oi, h, l);
-                *reinterpret_cast<uint2*>(d + 6 * kA2ArrBytes) = h;
-                *reinterpret_cast<uint2*>(d + 7 * kA2ArrBytes) = l;
-                fence_proxy_async_smem();
+                tmem_st2(ta + 192, h.x, h.y);
+                tmem_st2(ta + 192 + 8, l.x, l.y);
+                tmem_st_wait();
+                tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&full2[c]);
             }

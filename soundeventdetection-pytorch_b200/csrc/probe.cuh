@@ -39,14 +39,39 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const float* __restr
         mbar_init(&bar, 1);
         mbar_fence_init();
     }
-    if (warp == 0) tmem_alloc<256>(&tmem_ptr);
+    if (warp == 0) tmem_alloc<512>(&tmem_ptr);
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_ptr;
 
-    if (tid == 0) {
+    if (a_major == 2) {
+        // A through tensor memory: thread (row m) packs its K values two per column into TMEM columns 256.. and the
+        // MMA reads them from there (K-major by construction)
+        const int m = warp * 32 + lane;
+        const uint32_t ta = tmem + 256 + (static_cast<uint32_t>(warp * 32) << 16);
+        for (int k = 0; k < K; k += 4) {
+            uint32_t w[2];
+            for (int h = 0; h < 2; ++h) {
+                const __nv_bfloat162 v = __floats2bfloat162_rn(a[m * K + k + 2 * h], a[m * K + k + 2 * h + 1]);
+                w[h] = *reinterpret_cast<const uint32_t*>(&v);
+            }
+            tmem_st2(ta + k / 2, w[0], w[1]);
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (tid == 0) {
+            const uint32_t idesc = make_idesc(kFmtBF16, kMajorK, b_major, 128, N, 0, neg_b);
+            for (int ks = 0; ks < K / 16; ++ks) {
+                const uint32_t b_addr = smem_u32(b_s) + ks * 2 * b_lbo;
+                umma_f16_ts(tmem, tmem + 256 + ks * 8, make_smem_desc(b_addr, b_lbo, sbo), idesc, ks > 0 ? 1u : 0u);
+            }
+            umma_commit(&bar);
+        }
+    } else if (tid == 0) {
         const uint32_t idesc = make_idesc(kFmtBF16, a_major, b_major, 128, N, 0, neg_b);
         for (int ks = 0; ks < K / 16; ++ks) {
             const uint32_t a_addr = smem_u32(a_s) + ks * 2 * a_lbo;
@@ -70,7 +95,7 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const float* __restr
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        tmem_dealloc<256>(tmem);
+        tmem_dealloc<512>(tmem);
     }
 }
 

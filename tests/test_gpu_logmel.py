@@ -37,9 +37,11 @@ def gpu_logmel(y, **kw):
 
 
 @pytest.mark.parametrize("N,K,am,bm,pad,neg", [(128, 16, 0, 0, 0, 0), (128, 64, 0, 1, 0, 0), (256, 64, 0, 0, 0, 0),
-                                               (128, 32, 0, 1, 16, 0), (64, 32, 1, 0, 0, 0), (32, 48, 0, 0, 0, 1)])
+                                               (128, 32, 0, 1, 16, 0), (64, 32, 1, 0, 0, 0), (32, 48, 0, 0, 0, 1),
+                                               (128, 64, 2, 0, 0, 0), (128, 32, 2, 1, 0, 0)])
 def test_umma_descriptor_conventions(N, K, am, bm, pad, neg):
-    """Pins the tcgen05 shared-memory descriptor conventions the kernels rely on (see csrc/umma.cuh)."""
+    """Pins the tcgen05 shared-memory descriptor conventions the kernels rely on (see csrc/umma.cuh); am == 2 feeds
+    the A operand from tensor memory (tcgen05.st + the [a_tmem] MMA form)."""
     g = torch.Generator().manual_seed(N + K)
     a = torch.randn(128, K, generator=g).cuda()
     b = torch.randn(K, N, generator=g).cuda()
