@@ -42,6 +42,7 @@ def build(force: bool = False, fp16: bool | None = None, verbose: bool = False) 
     cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xptxas", "-v" if verbose else "-warn-spills", "--shared", "-Xcompiler", "-fPIC",
            f"-DSEDB_SPLIT_FP16={1 if fp16 else 0}", "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += os.environ.get("SEDB_EXTRA_NVCC_FLAGS", "").split()          # development experiments only
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

@@ -22,6 +22,10 @@
 #pragma once
 #include "umma.cuh"
 
+#ifndef SEDB_L2_PREFETCH
+#define SEDB_L2_PREFETCH 1
+#endif
+
 namespace sedb {
 
 constexpr int kSampleRate = 48000;
@@ -41,12 +45,13 @@ constexpr int kA1ChunkBytes = 4 * kA1ArrBytes;             // cH | cL | sH | sL 
 constexpr int kB1Sbo = 144;                                // padded stride between 8-sample groups (bank spread)
 constexpr int kB1Lbo = 16 * kB1Sbo;                        // 2304: stride between groups of 8 rows (K)
 constexpr int kB1ArrBytes = 2 * kB1Lbo;                    // 4608
-constexpr int kSlotBytes = kA1ChunkBytes + 4 * kB1ArrBytes; // 34816: stage 1 (A1 + UH UL VH VL); stage 2 uses 8 x 4 KB
+constexpr int kB1SlotBytes = 4 * kB1ArrBytes;              // 18432: UH UL VH VL of one stage-1 chunk
 constexpr int kNumSlots = 4;
-constexpr int kRingBytes = kSlotBytes * kNumSlots;         // 139264 (the power spectrum aliases the ring)
+constexpr int kA1RingBytes = kA1ChunkBytes * kNumSlots;    // 65536: stage-1 constant chunks (bulk copies, run ahead of the frame)
+constexpr int kB1RingBytes = kB1SlotBytes * kNumSlots;     // 73728: stage-1 data operand chunks; the power spectrum aliases it
+constexpr int kRingBytes = kA1RingBytes + kB1RingBytes;    // 139264
 constexpr int kA2ArrBytes = 128 * 16 * 2;                  // 4 KB
 static_assert((kNumSlots & (kNumSlots - 1)) == 0, "slot index uses a mask");
-static_assert(8 * kA2ArrBytes <= kSlotBytes, "stage-2 operands must fit a slot");
 
 constexpr int kOffB2 = 0;
 constexpr int kOffRing = kOffB2 + kB2Bytes;                // 65536
@@ -67,7 +72,7 @@ constexpr int kOffE1Tw = kOffHannLane + 1024;              // exp(-2 pi i n/128)
 constexpr int kOffBars = kOffE1Tw + 512;                   // mbarriers
 constexpr int kOffTmem = kOffBars + 256;                   // tmem base address
 constexpr int kSmemBytes = kOffTmem + 16;
-static_assert(kRingBytes >= (kBins + 3) * 4, "power spectrum must fit in the ring");
+static_assert(kB1RingBytes >= (kBins + 3) * 4, "power spectrum must fit in the data operand ring");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
 constexpr int kWorkerWarps = 16;
@@ -223,8 +228,9 @@ template <int MODE>   // 0: log-mel output; 1: complex STFT output
 __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* b2_s = smem + kOffB2;
-    uint8_t* ring = smem + kOffRing;
-    float* p_s = reinterpret_cast<float*>(ring);
+    uint8_t* a1ring = smem + kOffRing;
+    uint8_t* b1ring = a1ring + kA1RingBytes;
+    float* p_s = reinterpret_cast<float*>(b1ring);
     float* alt_s = reinterpret_cast<float*>(smem + kOffAlt);
     float* x128_s = reinterpret_cast<float*>(smem + kOffX128);
     float* v_s = reinterpret_cast<float*>(smem + kOffV);
@@ -245,7 +251,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
     uint64_t* full2 = bars + 8;      // [4] stage-2 slot filled (4 worker warps)
     uint64_t* d1_full = bars + 12;   // stage-1 accumulators complete
     uint64_t* d2_full = bars + 13;   // stage-2 accumulators complete
-    uint64_t* ring_free = bars + 14; // workers finished the frame (power spectrum no longer aliases the ring)
     uint64_t* b2_full = bars + 15;   // resident stage-2 constants landed
 
     const int tid = threadIdx.x;
@@ -260,7 +265,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         }
         mbar_init(d1_full, 1);
         mbar_init(d2_full, 1);
-        mbar_init(ring_free, kWorkerWarps);
         mbar_init(b2_full, 1);
         mbar_fence_init();
     }
@@ -307,7 +311,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         }
         __syncwarp();
         for (int it = 0; it < n_iter; ++it) {
-            if (it > 0) mbar_wait(ring_free, (it - 1) & 1);
 #pragma unroll 1
             for (int c = 0; c < 8; ++c) {
                 const int g = it * 8 + c;
@@ -316,12 +319,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 mbar_wait(&empty1[s], (u & 1) ^ 1);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&full1[s], kA1ChunkBytes);
-                    bulk_g2s(ring + s * kSlotBytes, prm.a1 + c * kA1ChunkBytes, kA1ChunkBytes, &full1[s]);
+                    bulk_g2s(a1ring + s * kA1ChunkBytes, prm.a1 + c * kA1ChunkBytes, kA1ChunkBytes, &full1[s]);
                 }
                 __syncwarp();
             }
             // pull the next frame's samples towards L2 while this one is being processed
-            if (it + 1 < n_iter) {
+            if (SEDB_L2_PREFETCH && it + 1 < n_iter) {
                 const long long f = blockIdx.x + static_cast<long long>(it + 1) * gridDim.x;
                 const int clip = static_cast<int>(f / prm.n_frames);
                 const int t = static_cast<int>(f - static_cast<long long>(clip) * prm.n_frames);
@@ -344,14 +347,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         if (tmem != 0) __trap();
         constexpr uint32_t idesc1 = make_idesc(kSplitFmt, kMajorK, kMajorMN, 128, 128);
         constexpr uint32_t idesc2 = make_idesc(kSplitFmt, kMajorK, kMajorK, 128, 128);
-        const uint32_t ring_a = smem_u32(ring);
         const uint32_t b2_a = smem_u32(b2_s);
         // descriptors for slot 0 / K-chunk 0; other slots and chunks add to the start-address field (16-byte units)
-        const uint64_t dA1 = make_smem_desc(ring_a, 2048, 128);                         // cH; cL, sH, sL follow
-        const uint64_t dB1 = make_smem_desc(ring_a + kA1ChunkBytes, kB1Lbo, kB1Sbo);     // uH; uL, vH, vL follow
+        const uint64_t dA1 = make_smem_desc(smem_u32(a1ring), 2048, 128);               // cH; cL, sH, sL follow
+        const uint64_t dB1 = make_smem_desc(smem_u32(b1ring), kB1Lbo, kB1Sbo);          // uH; uL, vH, vL follow
         const uint64_t dB2 = make_smem_desc(b2_a, 2048, 128);                           // reH; reL, imH, imL follow
         constexpr uint32_t kA1Step = kA1ArrBytes >> 4, kB1Step = kB1ArrBytes >> 4;
-        constexpr uint32_t kB2Step = kB2ArrBytes >> 4, kSlotStep = kSlotBytes >> 4;
+        constexpr uint32_t kB2Step = kB2ArrBytes >> 4, kA1SlotStep = kA1ChunkBytes >> 4, kB1SlotStep = kB1SlotBytes >> 4;
         mbar_wait(b2_full, 0);
         for (int it = 0; it < n_iter; ++it) {
             // ---------------- stage 1: 8 K-chunks of 16 folded rows (m)
@@ -363,7 +365,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 mbar_wait(&full1[s], u & 1);
                 tc_fence_after();
                 if (elect_one()) {
-                    const uint64_t a = dA1 + s * kSlotStep, bb = dB1 + s * kSlotStep;
+                    const uint64_t a = dA1 + s * kA1SlotStep, bb = dB1 + s * kB1SlotStep;
                     const uint32_t acc = (c > 0) ? 1u : 0u;
                     umma_f16(0, a, bb, idesc1, acc);                                   // cH uH
                     umma_f16(0, a + kA1Step, bb, idesc1, 1u);                          // cL uH
@@ -434,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
 
         // stage-1 producer mapping: warp -> row r of the 16-row chunk, lane -> 4 consecutive samples
         const int r = warp;
-        const uint32_t b1_off = kA1ChunkBytes + (lane >> 1) * kB1Sbo + (r >> 3) * kB1Lbo + (r & 7) * 16 + (lane & 1) * 8;
+        const uint32_t b1_off = (lane >> 1) * kB1Sbo + (r >> 3) * kB1Lbo + (r & 7) * 16 + (lane & 1) * 8;
         const float alt_sign = (r & 1) ? -1.f : 1.f;
 
         long long tprev = clock64();
@@ -460,12 +462,30 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 v.w = __ldg(y + reflect_index(j0 + 3, L));
                 return v;
             };
+            // interior frames (every in-window sample inside the clip, 16-byte aligned rows: all but the first and last
+            // frames of a clip): straight-line vector loads off two base pointers; only chunk 0 touches rows that are
+            // partly outside the window.  Edge frames take the general path (reflect padding, scalar loads).
+            const bool interior = vec_ok && t >= 1 && static_cast<long long>(t) * kHop + (kWin / 2) <= L;
+            if (interior) {
+                const float* fr = y + (static_cast<long long>(t) * kHop - kPadRefl) + 4 * lane;
+                const float4* pa = reinterpret_cast<const float4*>(fr + 128 * r);                 // row 16 c + r: + 512 c
+                const float4* pb = reinterpret_cast<const float4*>(fr + 128 * (256 - r));         // row 256 - 16 c - r: - 512 c
+                const int na = 128 * r + 4 * lane, nb = 128 * (r == 0 ? 128 : 256 - r) + 4 * lane;
+                xa[0] = (na >= kLpad) ? __ldg(pa) : make_float4(0.f, 0.f, 0.f, 0.f);
+                xb[0] = (nb < kLpad + kWin) ? __ldg(r == 0 ? pb - 32 * 128 : pb) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int m = 16 * c + r;
-                const int mb = (m == 0) ? 128 : 256 - m;
-                xa[c] = load4(128 * m + 4 * lane);
-                xb[c] = load4(128 * mb + 4 * lane);
+                for (int c = 1; c < 8; ++c) {
+                    xa[c] = __ldg(pa + 512 * c);
+                    xb[c] = __ldg(pb - 512 * c);
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const int m = 16 * c + r;
+                    const int mb = (m == 0) ? 128 : 256 - m;
+                    xa[c] = load4(128 * m + 4 * lane);
+                    xb[c] = load4(128 * mb + 4 * lane);
+                }
             }
             // ---------------------------------------------------------------- per-frame block scale (fp16 halves)
             float scale = 1.0f, inv_scale = 1.0f, sqrt_scale = 1.0f;
@@ -535,7 +555,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 split_pack2(v01, vh[0], vl[0]);
                 split_pack2(v23, vh[1], vl[1]);
                 mbar_wait(&empty1[s], (u & 1) ^ 1);
-                uint8_t* dst = ring + s * kSlotBytes + b1_off;
+                uint8_t* dst = b1ring + s * kB1SlotBytes + b1_off;
                 *reinterpret_cast<uint2*>(dst + 0 * kB1ArrBytes) = make_uint2(uh[0], uh[1]);
                 *reinterpret_cast<uint2*>(dst + 1 * kB1ArrBytes) = make_uint2(ul[0], ul[1]);
                 *reinterpret_cast<uint2*>(dst + 2 * kB1ArrBytes) = make_uint2(vh[0], vh[1]);
@@ -701,7 +721,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 SEDB_PROF(9);
                 worker_sync();
                 SEDB_PROF(10);
-                if (lane == 0) mbar_arrive(ring_free);               // p_s is dead: the ring may be refilled
                 float* out_row = prm.out + (static_cast<long long>(clip) * prm.n_frames + t) * kMel;
                 mel_finalize<kWorkerThreads / kMel>(part_s, mel_tab_s, coef_s, prm.norm != nullptr ? norm_s : nullptr,
                                                     inv_scale * inv_scale, out_row, tid);
@@ -709,7 +728,6 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
             }
             if (MODE != 0) {
                 worker_sync();                                        // stores of this frame done
-                if (lane == 0) mbar_arrive(ring_free);
             }
             SEDB_PROF(7);   // mel + dB
         }
