@@ -29,6 +29,7 @@ namespace sedb {
     } while (0)
 
 constexpr int kConvThreads = 320;          // 8 epilogue warps + MMA warp + copy warp
+constexpr int kConvMaxTiles = 4;            // M tiles (128 pixels) per work item
 constexpr int kConvMaxWSlots = 6;
 constexpr int kConvMaxWSlotBytes = 16384;  // weight ring slot: `kpb` consecutive (tap, 16-channel) blocks of hi|lo x [cout_tile][16]
 constexpr int kConvLead = 8;
@@ -225,16 +226,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                                 for (int j = 0; j < p.kpb; ++j) {
                                     const uint64_t bL = bH + b_lo_delta;
                                     const uint32_t acc = (kc > 0 || tap > 0 || ks0 + j > 0) ? 1u : 0u;
-                                    uint64_t aH = a_base + (2 * (ks0 + j) * p.P + tap_off);
-                                    uint32_t d = acc_base;
-#pragma unroll 1
-                                    for (int m = 0; m < p.n_tiles; ++m) {
-                                        const uint64_t aL = aH + a_lo_delta;
-                                        umma_f16(d, aH, bH, idesc, acc);
-                                        umma_f16(d, aL, bH, idesc, 1u);
-                                        umma_f16(d, aH, bL, idesc, 1u);
-                                        aH += 128;
-                                        d += p.cout_tile;
+                                    // tiles unrolled with immediate operand offsets: the single issuing lane must
+                                    // not spend more instructions per MMA than a narrow (N = 32) MMA takes to run
+                                    const uint64_t aH = a_base + (2 * (ks0 + j) * p.P + tap_off);
+                                    const uint64_t aL = aH + a_lo_delta;
+                                    const uint32_t ct = p.cout_tile;
+#pragma unroll
+                                    for (int m = 0; m < kConvMaxTiles; ++m) {
+                                        if (m < p.n_tiles) {
+                                            umma_f16(acc_base + m * ct, aH + 128 * m, bH, idesc, acc);
+                                            umma_f16(acc_base + m * ct, aL + 128 * m, bH, idesc, 1u);
+                                            umma_f16(acc_base + m * ct, aH + 128 * m, bL, idesc, 1u);
+                                        }
                                     }
                                     bH += 2 * b_lo_delta;            // next 16-channel block of the group
                                 }

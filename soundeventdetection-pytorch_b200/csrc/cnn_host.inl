@@ -37,7 +37,7 @@ int plan_umma_layer(const UmmaLayer& L, int H, int W, sedb::ConvParams& p) {
     p.n_ntiles = L.cout / L.cout_tile;
     p.pool = L.pool;
     p.ntaps = L.ntaps;
-    int max_tiles = (L.cin_chunk <= 64) ? 4 : 2;
+    int max_tiles = (L.cin_chunk <= 64) ? sedb::kConvMaxTiles : 2;
     if (max_tiles * L.cout_tile > 256) max_tiles = 256 / L.cout_tile;   // accumulators are double buffered in TMEM
     return plan_umma_layer_tiles(L, H, W, max_tiles, p);
 }

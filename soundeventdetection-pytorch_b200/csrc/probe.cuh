@@ -121,6 +121,8 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(unsigned long long* o
     const uint32_t tmem = tmem_ptr;
     const int mode = lbo_b >> 24;          // 0: lane-0 branch, 1: converged warp + elect
     lbo_b &= 0xffffff;
+    const uint32_t a_off = static_cast<uint32_t>(lbo_a >> 24) * 16;   // A start offset (bytes, 16-byte units): tap shifts
+    lbo_a &= 0xffffff;
     if (mode == 0) {
         if (tid == 0) {
             const uint32_t idesc = make_idesc(kFmtF16, kMajorK, b_major, 128, N);
@@ -138,7 +140,7 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(unsigned long long* o
         // lane issues
         if (tmem != 0) __trap();
         const uint32_t idesc = make_idesc(kFmtF16, kMajorK, b_major, 128, N);
-        const uint64_t da = make_smem_desc(smem_u32(smem), lbo_a, 128);
+        const uint64_t da = make_smem_desc(smem_u32(smem) + a_off, lbo_a, 128);
         const uint64_t db = make_smem_desc(smem_u32(smem) + 32768, lbo_b, 128);
         const uint32_t amask = (n_acc >= 4) ? 3u : (n_acc >= 2 ? 1u : 0u);
         const long long t0 = clock64();
