@@ -82,6 +82,17 @@ int sedb_power_mel_db_f32(sedb_ctx_t* ctx, const float* spec_dev, long long rows
 int sedb_logmel_host_f32(sedb_ctx_t* ctx, const float* wave_host, long long n_clips, long long n_samples,
                          long long wave_stride, const float* norm_host, float* out_host);
 
+/* ---- 16-bit PCM input: read_multichannel_audio's channel handling fused into the loader -------------
+ * Replaces dataset/dataset_utils.py:63-74 (soundfile.read of a PCM_16 file = int16 / 32768, then
+ * `.mean(1)` because common_config.audio_channels == 1) followed by the fused log-mel above.
+ * pcm: [n_clips, clip_stride, n_channels] interleaved int16, i.e. the WAV data chunk as stored on disk
+ * (n_samples valid sample frames per clip, n_channels in 1..16; 1, 2 and 4 take the vector path).
+ * Halves the bytes a clip costs in HBM and over PCIe compared with float32 mono. */
+int sedb_logmel_pcm16(sedb_ctx_t* ctx, const int16_t* pcm_dev, long long n_clips, long long n_samples,
+                      long long clip_stride, int n_channels, const float* norm_dev, float* out_dev, void* stream);
+int sedb_logmel_host_pcm16(sedb_ctx_t* ctx, const int16_t* pcm_host, long long n_clips, long long n_samples,
+                           long long clip_stride, int n_channels, const float* norm_host, float* out_host);
+
 /* ---- spectrogram CNN: Cnn_AvgPooling (models/spectogram_models.py:163-205) ----------------------- */
 /* channels[i], pools[i]: model_config entries (spectogram_models.py:7, main.py:35); input channels = 1. */
 int sedb_cnn_create(sedb_ctx_t* ctx, const int* channels, const int* pools, int n_blocks, int classes_num,
@@ -127,6 +138,11 @@ int sedb_adam_amsgrad_step(float* param_dev, const float* grad_dev, float* exp_a
  * classes] float32 host.  H2D chunks, log-mel, CNN and the D2H of the probabilities are pipelined. */
 int sedb_sed_host_f32(sedb_ctx_t* ctx, sedb_cnn_t* cnn, const float* wave_host, long long n_clips,
                       long long n_samples, long long wave_stride, const float* norm_host, float* probs_host);
+
+/* the same from 16-bit PCM host buffers (see sedb_logmel_pcm16) */
+int sedb_sed_host_pcm16(sedb_ctx_t* ctx, sedb_cnn_t* cnn, const int16_t* pcm_host, long long n_clips,
+                        long long n_samples, long long clip_stride, int n_channels, const float* norm_host,
+                        float* probs_host);
 
 /* ---- diagnostics ---------------------------------------------------------------------------------- */
 /* One-CTA tcgen05 GEMM probe used by the GPU tests to pin the shared-memory descriptor conventions:

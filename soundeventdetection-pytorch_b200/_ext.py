@@ -32,6 +32,12 @@ _SIGNATURES = {
     "sedb_power_mel_db_f32": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_ll, c_float_p, c_float_p,
                                              ctypes.c_void_p]),
     "sedb_logmel_host_f32": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_ll, c_ll, c_ll, c_float_p, c_float_p]),
+    "sedb_logmel_pcm16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_ll, c_ll, c_ll, ctypes.c_int, c_float_p,
+                                         c_float_p, ctypes.c_void_p]),
+    "sedb_logmel_host_pcm16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_ll, c_ll, c_ll, ctypes.c_int,
+                                              c_float_p, c_float_p]),
+    "sedb_sed_host_pcm16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, c_ll, c_ll, c_ll,
+                                           ctypes.c_int, c_float_p, c_float_p]),
     "sedb_cnn_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int),
                                        ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "sedb_cnn_destroy": (ctypes.c_int, [ctypes.c_void_p]),

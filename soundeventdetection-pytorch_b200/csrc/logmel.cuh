@@ -84,8 +84,12 @@ constexpr int kWorkerRegs = 112;             // setmaxnreg: the service warp gro
 constexpr int kServiceRegs = 24;
 
 struct LogmelParams {
-    const float* wave;        // [B, wave_stride] fp32
-    long long wave_stride;    // elements between clips
+    const float* wave;        // IN 0: [B, wave_stride] fp32 mono
+    const int16_t* pcm;       // IN 1: [B, wave_stride, n_channels] interleaved 16-bit PCM (WAV data order); the kernel
+                              //       forms the mono mix mean_ch(s / 32768) (dataset_utils.py:67-74 with audio_channels = 1)
+    int n_channels;           // IN 1 only
+    float pcm_scale;          // IN 1 only: 1 / (32768 n_channels)
+    long long wave_stride;    // samples (sample frames) between clips
     int n_samples;            // valid samples per clip
     int n_clips;
     int n_frames;             // T = 1 + n_samples / hop
@@ -224,7 +228,26 @@ __device__ __forceinline__ void mel_finalize(const float* __restrict__ part_s, c
         }                                                                        \
     } while (0)
 
-template <int MODE>   // 0: log-mel output; 1: complex STFT output
+// 4 consecutive sample frames of interleaved 16-bit PCM -> mono floats (C in {1, 2, 4}: 8 C bytes, aligned)
+__device__ __forceinline__ float s16lo(uint32_t w) { return static_cast<float>(static_cast<short>(w & 0xffffu)); }
+__device__ __forceinline__ float s16hi(uint32_t w) { return static_cast<float>(static_cast<int>(w) >> 16); }
+__device__ __forceinline__ float4 pcm_mono4(const int16_t* __restrict__ p, int C, float scale) {
+    float4 v;
+    if (C == 1) {
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(p));
+        v = make_float4(s16lo(w.x), s16hi(w.x), s16lo(w.y), s16hi(w.y));
+    } else if (C == 2) {
+        const uint4 w = __ldg(reinterpret_cast<const uint4*>(p));
+        v = make_float4(s16lo(w.x) + s16hi(w.x), s16lo(w.y) + s16hi(w.y), s16lo(w.z) + s16hi(w.z), s16lo(w.w) + s16hi(w.w));
+    } else {
+        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+        v = make_float4((s16lo(a.x) + s16hi(a.x)) + (s16lo(a.y) + s16hi(a.y)), (s16lo(a.z) + s16hi(a.z)) + (s16lo(a.w) + s16hi(a.w)),
+                        (s16lo(b.x) + s16hi(b.x)) + (s16lo(b.y) + s16hi(b.y)), (s16lo(b.z) + s16hi(b.z)) + (s16lo(b.w) + s16hi(b.w)));
+    }
+    return make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+}
+
+template <int MODE, int IN>   // MODE 0: log-mel output; 1: complex STFT output.  IN 0: fp32 mono; 1: 16-bit PCM
 __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* b2_s = smem + kOffB2;
@@ -329,10 +352,18 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 const int clip = static_cast<int>(f / prm.n_frames);
                 const int t = static_cast<int>(f - static_cast<long long>(clip) * prm.n_frames);
                 const long long j0 = static_cast<long long>(t) * kHop + kLpad - kPadRefl;
-                const float* src = prm.wave + static_cast<long long>(clip) * prm.wave_stride + j0;
+                const void* src;
+                uint32_t nbytes;
+                if (IN == 0) {
+                    src = prm.wave + static_cast<long long>(clip) * prm.wave_stride + j0;
+                    nbytes = kWin * 4;
+                } else {
+                    src = prm.pcm + (static_cast<long long>(clip) * prm.wave_stride + j0) * prm.n_channels;
+                    nbytes = kWin * 2 * prm.n_channels;
+                }
                 if (j0 >= 0 && j0 + kWin <= prm.n_samples && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
                     if (elect_one())
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(kWin * 4) : "memory");
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(nbytes) : "memory");
                     __syncwarp();
                 }
             }
@@ -444,47 +475,88 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
             const long long f = blockIdx.x + static_cast<long long>(it) * gridDim.x;
             const int clip = static_cast<int>(f / prm.n_frames);
             const int t = static_cast<int>(f - static_cast<long long>(clip) * prm.n_frames);
-            const float* __restrict__ y = prm.wave + static_cast<long long>(clip) * prm.wave_stride;
             const int L = prm.n_samples;
-            const bool vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
 
             // ---------------------------------------------------------------- load the frame into registers
-            // chunk c, this thread: rows m = 16 c + r and 256 - m (row 128 for m = 0), samples n2 = 4 lane .. +3
+            // chunk c, this thread: rows m = 16 c + r and 256 - m (row 128 for m = 0), samples n2 = 4 lane .. +3.
+            // Interior frames (every in-window sample inside the clip, aligned rows: all but the first and last frames
+            // of a clip) use straight-line vector loads off two base pointers; only chunk 0 touches rows that are partly
+            // outside the window.  Edge frames take the general path (reflect padding, scalar loads).
             float4 xa[8], xb[8];
-            auto load4 = [&](int n0) -> float4 {
-                const int j0 = t * kHop + n0 - kPadRefl;
-                if (n0 < kLpad - 3 || n0 >= kLpad + kWin) return make_float4(0.f, 0.f, 0.f, 0.f);   // window is zero
-                if (vec_ok && j0 >= 0 && j0 + 4 <= L) return __ldg(reinterpret_cast<const float4*>(y + j0));
-                float4 v;
-                v.x = __ldg(y + reflect_index(j0 + 0, L));
-                v.y = __ldg(y + reflect_index(j0 + 1, L));
-                v.z = __ldg(y + reflect_index(j0 + 2, L));
-                v.w = __ldg(y + reflect_index(j0 + 3, L));
-                return v;
-            };
-            // interior frames (every in-window sample inside the clip, 16-byte aligned rows: all but the first and last
-            // frames of a clip): straight-line vector loads off two base pointers; only chunk 0 touches rows that are
-            // partly outside the window.  Edge frames take the general path (reflect padding, scalar loads).
-            const bool interior = vec_ok && t >= 1 && static_cast<long long>(t) * kHop + (kWin / 2) <= L;
-            if (interior) {
-                const float* fr = y + (static_cast<long long>(t) * kHop - kPadRefl) + 4 * lane;
-                const float4* pa = reinterpret_cast<const float4*>(fr + 128 * r);                 // row 16 c + r: + 512 c
-                const float4* pb = reinterpret_cast<const float4*>(fr + 128 * (256 - r));         // row 256 - 16 c - r: - 512 c
-                const int na = 128 * r + 4 * lane, nb = 128 * (r == 0 ? 128 : 256 - r) + 4 * lane;
-                xa[0] = (na >= kLpad) ? __ldg(pa) : make_float4(0.f, 0.f, 0.f, 0.f);
-                xb[0] = (nb < kLpad + kWin) ? __ldg(r == 0 ? pb - 32 * 128 : pb) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const bool inside = t >= 1 && static_cast<long long>(t) * kHop + (kWin / 2) <= L;
+            const int na = 128 * r + 4 * lane, nb = 128 * (r == 0 ? 128 : 256 - r) + 4 * lane;
+            if (IN == 0) {
+                const float* __restrict__ y = prm.wave + static_cast<long long>(clip) * prm.wave_stride;
+                const bool vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
+                auto load4 = [&](int n0) -> float4 {
+                    const int j0 = t * kHop + n0 - kPadRefl;
+                    if (n0 < kLpad - 3 || n0 >= kLpad + kWin) return make_float4(0.f, 0.f, 0.f, 0.f);   // window is zero
+                    if (vec_ok && j0 >= 0 && j0 + 4 <= L) return __ldg(reinterpret_cast<const float4*>(y + j0));
+                    float4 v;
+                    v.x = __ldg(y + reflect_index(j0 + 0, L));
+                    v.y = __ldg(y + reflect_index(j0 + 1, L));
+                    v.z = __ldg(y + reflect_index(j0 + 2, L));
+                    v.w = __ldg(y + reflect_index(j0 + 3, L));
+                    return v;
+                };
+                if (inside && vec_ok) {
+                    const float* fr = y + (static_cast<long long>(t) * kHop - kPadRefl) + 4 * lane;
+                    const float4* pa = reinterpret_cast<const float4*>(fr + 128 * r);             // row 16 c + r: + 512 c
+                    const float4* pb = reinterpret_cast<const float4*>(fr + 128 * (256 - r));     // row 256 - 16 c - r: - 512 c
+                    xa[0] = (na >= kLpad) ? __ldg(pa) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    xb[0] = (nb < kLpad + kWin) ? __ldg(r == 0 ? pb - 32 * 128 : pb) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-                for (int c = 1; c < 8; ++c) {
-                    xa[c] = __ldg(pa + 512 * c);
-                    xb[c] = __ldg(pb - 512 * c);
+                    for (int c = 1; c < 8; ++c) {
+                        xa[c] = __ldg(pa + 512 * c);
+                        xb[c] = __ldg(pb - 512 * c);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int m = 16 * c + r;
+                        xa[c] = load4(128 * m + 4 * lane);
+                        xb[c] = load4(128 * ((m == 0) ? 128 : 256 - m) + 4 * lane);
+                    }
                 }
             } else {
+                const int C = prm.n_channels;
+                const float ps = prm.pcm_scale;
+                const int16_t* __restrict__ y = prm.pcm + static_cast<long long>(clip) * prm.wave_stride * C;
+                const bool vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && (C == 1 || C == 2 || C == 4);
+                auto load4 = [&](int n0) -> float4 {
+                    const int j0 = t * kHop + n0 - kPadRefl;
+                    if (n0 < kLpad - 3 || n0 >= kLpad + kWin) return make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (vec_ok && j0 >= 0 && j0 + 4 <= L) return pcm_mono4(y + static_cast<long long>(j0) * C, C, ps);
+                    float v[4];
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const int m = 16 * c + r;
-                    const int mb = (m == 0) ? 128 : 256 - m;
-                    xa[c] = load4(128 * m + 4 * lane);
-                    xb[c] = load4(128 * mb + 4 * lane);
+                    for (int e = 0; e < 4; ++e) {
+                        const int16_t* q = y + static_cast<long long>(reflect_index(j0 + e, L)) * C;
+                        int acc = 0;
+                        for (int ch = 0; ch < C; ++ch) acc += __ldg(q + ch);
+                        v[e] = static_cast<float>(acc) * ps;
+                    }
+                    return make_float4(v[0], v[1], v[2], v[3]);
+                };
+                if (inside && vec_ok) {
+                    const int16_t* fr = y + (static_cast<long long>(t) * kHop - kPadRefl + 4 * lane) * C;
+                    const int16_t* pa = fr + 128 * r * C;
+                    const int16_t* pb = fr + 128 * (256 - r) * C;
+                    const int rowc = 128 * 16 * C;                                               // 16 rows
+                    xa[0] = (na >= kLpad) ? pcm_mono4(pa, C, ps) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    xb[0] = (nb < kLpad + kWin) ? pcm_mono4(r == 0 ? pb - 128 * 128 * C : pb, C, ps)
+                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                    for (int c = 1; c < 8; ++c) {
+                        xa[c] = pcm_mono4(pa + rowc * c, C, ps);
+                        xb[c] = pcm_mono4(pb - rowc * c, C, ps);
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const int m = 16 * c + r;
+                        xa[c] = load4(128 * m + 4 * lane);
+                        xb[c] = load4(128 * ((m == 0) ? 128 : 256 - m) + 4 * lane);
+                    }
                 }
             }
             // ---------------------------------------------------------------- per-frame block scale (fp16 halves)

@@ -125,9 +125,11 @@ int sedb_create(sedb_ctx_t** out_ctx) {
     CUDA_TRY(cudaMemcpy(c->b2, b2.data(), b2.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(c->mel_w, wts.data(), wts.size() * sizeof(float), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(c->mel_tab, tab.data(), tab.size() * sizeof(int4), cudaMemcpyHostToDevice));
-    CUDA_TRY(cudaFuncSetAttribute(sedb::logmel_fused_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(sedb::logmel_fused_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   sedb::kSmemBytes));
-    CUDA_TRY(cudaFuncSetAttribute(sedb::logmel_fused_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(sedb::logmel_fused_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  sedb::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(sedb::logmel_fused_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   sedb::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(sedb::power_mel_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   80 * 1024));
@@ -158,8 +160,10 @@ int sedb_destroy(sedb_ctx_t* c) {
     return 0;
 }
 
-static int launch_logmel(sedb_ctx_t* c, int mode, const float* wave, long long n_clips, long long n_samples,
-                         long long wave_stride, const float* norm, float* out, float* spec, cudaStream_t st) {
+// in_fmt 0: wave = float32 mono [n_clips, wave_stride]; 1: wave = int16 PCM [n_clips, wave_stride, n_channels]
+static int launch_logmel(sedb_ctx_t* c, int mode, const void* wave, long long n_clips, long long n_samples,
+                         long long wave_stride, const float* norm, float* out, float* spec, cudaStream_t st,
+                         int in_fmt = 0, int n_channels = 1) {
     if (!c) return fail("null context");
     if (n_clips < 0) return fail("negative clip count");
     if (n_clips == 0) return 0;
@@ -169,8 +173,12 @@ static int launch_logmel(sedb_ctx_t* c, int mode, const float* wave, long long n
                     SEDB_NFFT, sedb::kPadRefl);
     if (n_samples > 2000000000LL) return fail("n_samples too large");
     if (wave_stride < n_samples) return fail("wave_stride < n_samples");
+    if (in_fmt == 1 && (n_channels < 1 || n_channels > 16)) return fail("n_channels=%d: supported 1..16", n_channels);
     sedb::LogmelParams p;
-    p.wave = wave;
+    p.wave = in_fmt == 0 ? static_cast<const float*>(wave) : nullptr;
+    p.pcm = in_fmt == 1 ? static_cast<const int16_t*>(wave) : nullptr;
+    p.n_channels = n_channels;
+    p.pcm_scale = 1.0f / (32768.0f * static_cast<float>(n_channels));
     p.wave_stride = wave_stride;
     p.n_samples = static_cast<int>(n_samples);
     p.n_clips = static_cast<int>(n_clips);
@@ -186,10 +194,14 @@ static int launch_logmel(sedb_ctx_t* c, int mode, const float* wave, long long n
     p.prof = g_prof;
     const long long total = n_clips * p.n_frames;
     const int grid = static_cast<int>(total < c->num_sms ? total : c->num_sms);
-    if (mode == 0)
-        sedb::logmel_fused_kernel<0><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
+    if (mode == 0 && in_fmt == 0)
+        sedb::logmel_fused_kernel<0, 0><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
+    else if (mode == 0)
+        sedb::logmel_fused_kernel<0, 1><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
+    else if (in_fmt == 0)
+        sedb::logmel_fused_kernel<1, 0><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
     else
-        sedb::logmel_fused_kernel<1><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
+        return fail("the complex STFT output takes float32 input");
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -236,7 +248,7 @@ static int ensure_pipeline(sedb_ctx_t* c, size_t stage_elems, size_t out_elems) 
         for (int i = 0; i < 2; ++i) {
             cudaFree(c->stage[i]);
             c->stage[i] = nullptr;
-            CUDA_TRY(cudaMalloc(&c->stage[i], stage_elems * sizeof(float)));
+            CUDA_TRY(cudaMalloc(&c->stage[i], stage_elems * sizeof(float)));   // (sized in 4-byte units)
         }
         c->stage_elems = stage_elems;
     }
@@ -251,20 +263,24 @@ static int ensure_pipeline(sedb_ctx_t* c, size_t stage_elems, size_t out_elems) 
 
 // Shared body: H2D in chunks of clips (double buffered) overlapped with the fused log-mel kernel; optional CNN
 // on the resident log-mel image; one D2H of the result.
-static int run_host_pipeline(sedb_ctx_t* c, sedb_cnn_t* cnn, const float* wave_host, long long n_clips,
-                             long long n_samples, long long wave_stride, const float* norm_host, float* result_host) {
+static int run_host_pipeline(sedb_ctx_t* c, sedb_cnn_t* cnn, const void* wave_host, long long n_clips,
+                             long long n_samples, long long wave_stride, const float* norm_host, float* result_host,
+                             int in_fmt = 0, int n_channels = 1) {
     if (!c) return fail("null context");
     if (!wave_host || !result_host) return fail("null buffer");
     if (n_clips <= 0) return n_clips == 0 ? 0 : fail("negative clip count");
     if (n_samples <= sedb::kPadRefl) return fail("n_samples must exceed %d", sedb::kPadRefl);
     if (wave_stride < n_samples) return fail("wave_stride < n_samples");
     const long long T = sedb_num_frames(n_samples);
+    if (in_fmt == 1 && (n_channels < 1 || n_channels > 16)) return fail("n_channels=%d: supported 1..16", n_channels);
+    // bytes per sample frame: float32 mono or interleaved 16-bit PCM
+    const size_t fb = in_fmt == 0 ? sizeof(float) : 2 * static_cast<size_t>(n_channels);
     // chunk ~ 64 MB of waveform: long enough to saturate PCIe, short enough to overlap with compute
-    long long chunk = (64LL << 20) / (n_samples * 4);
+    long long chunk = (64LL << 20) / (n_samples * static_cast<long long>(fb));
     if (chunk < 1) chunk = 1;
     if (chunk > n_clips) chunk = n_clips;
-    const size_t samples_padded = (static_cast<size_t>(n_samples) + 3) & ~static_cast<size_t>(3);
-    if (int rc = ensure_pipeline(c, static_cast<size_t>(chunk) * samples_padded,
+    const size_t samples_padded = (static_cast<size_t>(n_samples) + 7) & ~static_cast<size_t>(7);   // 16-byte rows
+    if (int rc = ensure_pipeline(c, (static_cast<size_t>(chunk) * samples_padded * fb + 3) / 4,
                                  static_cast<size_t>(n_clips) * T * SEDB_MEL_BINS))
         return rc;
     const float* norm_dev = nullptr;
@@ -278,14 +294,14 @@ static int run_host_pipeline(sedb_ctx_t* c, sedb_cnn_t* cnn, const float* wave_h
         const long long nc = (n_clips - c0 < chunk) ? (n_clips - c0) : chunk;
         // the staging buffer may still be read by the kernel launched two chunks ago
         CUDA_TRY(cudaStreamWaitEvent(c->s_copy, c->ev_done[buf], 0));
-        CUDA_TRY(cudaMemcpy2DAsync(c->stage[buf], samples_padded * sizeof(float), wave_host + c0 * wave_stride,
-                                   static_cast<size_t>(wave_stride) * sizeof(float),
-                                   static_cast<size_t>(n_samples) * sizeof(float), static_cast<size_t>(nc),
-                                   cudaMemcpyHostToDevice, c->s_copy));
+        CUDA_TRY(cudaMemcpy2DAsync(c->stage[buf], samples_padded * fb,
+                                   static_cast<const uint8_t*>(wave_host) + static_cast<size_t>(c0 * wave_stride) * fb,
+                                   static_cast<size_t>(wave_stride) * fb, static_cast<size_t>(n_samples) * fb,
+                                   static_cast<size_t>(nc), cudaMemcpyHostToDevice, c->s_copy));
         CUDA_TRY(cudaEventRecord(c->ev_h2d[buf], c->s_copy));
         CUDA_TRY(cudaStreamWaitEvent(c->s_comp, c->ev_h2d[buf], 0));
         if (int rc = launch_logmel(c, 0, c->stage[buf], nc, n_samples, static_cast<long long>(samples_padded), norm_dev,
-                                   c->d_out + c0 * T * SEDB_MEL_BINS, nullptr, c->s_comp))
+                                   c->d_out + c0 * T * SEDB_MEL_BINS, nullptr, c->s_comp, in_fmt, n_channels))
             return rc;
         CUDA_TRY(cudaEventRecord(c->ev_done[buf], c->s_comp));
     }
@@ -308,6 +324,25 @@ int sedb_sed_host_f32(sedb_ctx_t* ctx, sedb_cnn_t* cnn, const float* wave_host, 
                       long long n_samples, long long wave_stride, const float* norm_host, float* probs_host) {
     if (!cnn) return fail("null cnn handle");
     return run_host_pipeline(ctx, cnn, wave_host, n_clips, n_samples, wave_stride, norm_host, probs_host);
+}
+
+/* ---- 16-bit PCM input (the WAV data chunk as it is on disk), channel mean fused into the loader --------------- */
+int sedb_logmel_pcm16(sedb_ctx_t* ctx, const int16_t* pcm_dev, long long n_clips, long long n_samples,
+                      long long clip_stride, int n_channels, const float* norm_dev, float* out_dev, void* stream) {
+    return launch_logmel(ctx, 0, pcm_dev, n_clips, n_samples, clip_stride, norm_dev, out_dev, nullptr,
+                         static_cast<cudaStream_t>(stream), 1, n_channels);
+}
+
+int sedb_logmel_host_pcm16(sedb_ctx_t* ctx, const int16_t* pcm_host, long long n_clips, long long n_samples,
+                           long long clip_stride, int n_channels, const float* norm_host, float* out_host) {
+    return run_host_pipeline(ctx, nullptr, pcm_host, n_clips, n_samples, clip_stride, norm_host, out_host, 1, n_channels);
+}
+
+int sedb_sed_host_pcm16(sedb_ctx_t* ctx, sedb_cnn_t* cnn, const int16_t* pcm_host, long long n_clips,
+                        long long n_samples, long long clip_stride, int n_channels, const float* norm_host,
+                        float* probs_host) {
+    if (!cnn) return fail("null cnn handle");
+    return run_host_pipeline(ctx, cnn, pcm_host, n_clips, n_samples, clip_stride, norm_host, probs_host, 1, n_channels);
 }
 
 int sedb_adam_amsgrad_step(float* param_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev,

@@ -73,8 +73,42 @@ def _norm_tensor(mean, std):
     return torch.cat([m, s]).contiguous()
 
 
+def _is_int16(x) -> bool:
+    return (isinstance(x, torch.Tensor) and x.dtype == torch.int16) or (isinstance(x, np.ndarray) and x.dtype == np.int16)
+
+
+def pcm16_to_log_mel(pcm, mean=None, std=None) -> torch.Tensor:
+    """Fused log-mel straight from 16-bit PCM (the WAV data chunk): ``[B, samples]`` or ``[B, samples, channels]`` int16
+    -> ``[B, T, 64]`` float32 CUDA.  The kernel forms the mono mix ``mean_ch(s / 32768)`` while loading, which is what
+    the reference's ``read_multichannel_audio`` produces for ``audio_channels == 1`` (dataset_utils.py:67-74:
+    ``soundfile.read`` scales PCM_16 by 1/32768, then ``.mean(1)``).  Half the bytes of the float32 path in HBM."""
+    if not _is_int16(pcm):
+        raise ValueError("pcm16_to_log_mel expects int16 samples")
+    x = pcm if isinstance(pcm, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pcm))
+    x = x.cuda() if not x.is_cuda else x
+    if x.dim() == 2:
+        x = x[:, :, None]
+    if x.dim() != 3:
+        raise ValueError("pcm16_to_log_mel expects [B, samples] or [B, samples, channels]")
+    x = x.contiguous()
+    B, n, C = x.shape
+    if not 1 <= C <= 16:
+        raise ValueError("1..16 interleaved channels are supported")
+    norm = _norm_tensor(mean, std)
+    out = torch.empty((B, num_frames(n), cfg.mel_bins), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        _ext.check(_ext.load().sedb_logmel_pcm16(_ext.context(), _ptr(x), B, n, n, C, _ptr(norm), _ptr(out),
+                                                 _ext.stream_ptr()))
+    return out
+
+
 def waveform_to_log_mel(wave, mean=None, std=None) -> torch.Tensor:
-    """Fused log-mel of a batch of mono clips: ``[B, samples]`` (or ``[samples]``) -> ``[B, T, 64]`` float32 CUDA."""
+    """Fused log-mel of a batch of mono clips: ``[B, samples]`` (or ``[samples]``) -> ``[B, T, 64]`` float32 CUDA.
+    int16 input is taken as 16-bit PCM (see :func:`pcm16_to_log_mel`)."""
+    if _is_int16(wave):
+        one = wave.ndim == 1
+        out = pcm16_to_log_mel(wave[None] if one else wave, mean, std)
+        return out[0] if one else out
     w = _as_cuda_f32(wave)
     squeeze = w.dim() == 1
     if squeeze:
