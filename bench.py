@@ -290,6 +290,45 @@ def run_ours(args):
     e2e_ok = bool(torch.allclose(host_probs, probs[:Ce].cpu(), atol=1e-4))
     e2e_value = world * Ce * CLIP_SECONDS / 3600.0 / (e2e_ms * 1e-3)
 
+    # ---- the same clips as 16-bit PCM (the WAV data chunk): not the headline configuration, reported
+    # beside it because it halves the bytes per clip in HBM and over PCIe
+    pcm16 = None
+    if not args.no_pcm16:
+        pcm_dev = (wave * 32767.0).round_().to(torch.int16)
+        from sed_b200.dataset.spectogram.preprocess import pcm16_to_log_mel
+        for _ in range(2):
+            pcm16_to_log_mel(pcm_dev, mean, std)
+        pa, pb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        pa.record()
+        for _ in range(e2e_steps):
+            pcm16_to_log_mel(pcm_dev, mean, std)
+        pb.record()
+        torch.cuda.synchronize()
+        pcm_lm_ms = pa.elapsed_time(pb) / e2e_steps
+        host_pcm = torch.empty(Ce, CLIP_SAMPLES, dtype=torch.int16).pin_memory()
+        host_pcm.copy_(pcm_dev[:Ce])
+        del pcm_dev
+
+        def pcm_step():
+            _ext.check(lib.sedb_sed_host_pcm16(_ext.context(), handle, ctypes.c_void_p(host_pcm.data_ptr()), Ce,
+                                               CLIP_SAMPLES, CLIP_SAMPLES, 1, ctypes.c_void_p(host_norm.data_ptr()),
+                                               ctypes.c_void_p(host_probs.data_ptr())))
+
+        pcm_step()
+        torch.cuda.synchronize()
+        parallel.barrier()
+        w0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            pcm_step()
+        pcm_ms = parallel.max_over_ranks((time.perf_counter() - w0) * 1e3 / e2e_steps, dev)
+        pcm16 = {"note": "same clips quantised to 16-bit PCM mono (sedb_logmel_pcm16 / sedb_sed_host_pcm16); "
+                         "not the headline configuration",
+                 "logmel_ms_device_resident": pcm_lm_ms,
+                 "e2e": {"value": world * Ce * CLIP_SECONDS / 3600.0 / (pcm_ms * 1e-3), "unit": "audio-hours/sec",
+                         "ms_per_step": pcm_ms, "h2d_bytes_per_step": Ce * CLIP_SAMPLES * 2 + 512,
+                         "d2h_bytes_per_step": Ce * 176 * 4, "clips_per_step": Ce}}
+
     if rank != 0:
         return
     hbm_peak, tf_peak, src = measured_peaks()
@@ -316,6 +355,8 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if pcm16 is not None:
+        line["pcm16"] = pcm16
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     emit(line)
@@ -350,6 +391,7 @@ def main():
     ap.add_argument("--e2e-clips", type=int, default=256)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pcm16", action="store_true", help="skip the 16-bit PCM variant of the measurement")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

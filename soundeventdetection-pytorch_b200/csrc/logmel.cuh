@@ -228,26 +228,78 @@ __device__ __forceinline__ void mel_finalize(const float* __restrict__ part_s, c
         }                                                                        \
     } while (0)
 
-// 4 consecutive sample frames of interleaved 16-bit PCM -> mono floats (C in {1, 2, 4}: 8 C bytes, aligned)
+// 4 consecutive sample frames of interleaved 16-bit PCM (C in {1, 2, 4}: 8 C bytes, aligned) -> mono floats.  The raw
+// load and the conversion are separate so that all loads of a batch are in flight before the first conversion waits.
 __device__ __forceinline__ float s16lo(uint32_t w) { return static_cast<float>(static_cast<short>(w & 0xffffu)); }
 __device__ __forceinline__ float s16hi(uint32_t w) { return static_cast<float>(static_cast<int>(w) >> 16); }
-__device__ __forceinline__ float4 pcm_mono4(const int16_t* __restrict__ p, int C, float scale) {
-    float4 v;
-    if (C == 1) {
-        const uint2 w = __ldg(reinterpret_cast<const uint2*>(p));
-        v = make_float4(s16lo(w.x), s16hi(w.x), s16lo(w.y), s16hi(w.y));
-    } else if (C == 2) {
-        const uint4 w = __ldg(reinterpret_cast<const uint4*>(p));
-        v = make_float4(s16lo(w.x) + s16hi(w.x), s16lo(w.y) + s16hi(w.y), s16lo(w.z) + s16hi(w.z), s16lo(w.w) + s16hi(w.w));
-    } else {
-        const uint4 a = __ldg(reinterpret_cast<const uint4*>(p)), b = __ldg(reinterpret_cast<const uint4*>(p) + 1);
-        v = make_float4((s16lo(a.x) + s16hi(a.x)) + (s16lo(a.y) + s16hi(a.y)), (s16lo(a.z) + s16hi(a.z)) + (s16lo(a.w) + s16hi(a.w)),
-                        (s16lo(b.x) + s16hi(b.x)) + (s16lo(b.y) + s16hi(b.y)), (s16lo(b.z) + s16hi(b.z)) + (s16lo(b.w) + s16hi(b.w)));
+template <int C>
+struct PcmRaw {
+    uint32_t w[2 * C];
+};
+template <int C>
+__device__ __forceinline__ PcmRaw<C> pcm_load_raw(const int16_t* __restrict__ p, bool live) {
+    PcmRaw<C> r;
+#pragma unroll
+    for (int i = 0; i < 2 * C; ++i) r.w[i] = 0u;
+    if (live) {
+        if (C == 1) {
+            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+            r.w[0] = v.x; r.w[1] = v.y;
+        } else {
+#pragma unroll
+            for (int q = 0; q < C / 2; ++q) {
+                const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + q);
+                r.w[4 * q] = v.x; r.w[4 * q + 1] = v.y; r.w[4 * q + 2] = v.z; r.w[4 * q + 3] = v.w;
+            }
+        }
     }
-    return make_float4(v.x * scale, v.y * scale, v.z * scale, v.w * scale);
+    return r;
+}
+template <int C>
+__device__ __forceinline__ float4 pcm_to_mono4(const PcmRaw<C>& r, float scale) {
+    float v[4];
+    if (C == 1) {
+        v[0] = s16lo(r.w[0]); v[1] = s16hi(r.w[0]); v[2] = s16lo(r.w[1]); v[3] = s16hi(r.w[1]);
+    } else if (C == 2) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = s16lo(r.w[e]) + s16hi(r.w[e]);
+    } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            v[e] = (s16lo(r.w[2 * e]) + s16hi(r.w[2 * e])) + (s16lo(r.w[2 * e + 1]) + s16hi(r.w[2 * e + 1]));
+    }
+    return make_float4(v[0] * scale, v[1] * scale, v[2] * scale, v[3] * scale);
+}
+// whole interior frame of this thread: 16 positions (xa[0..7], xb[0..7]) in batches of kBatch raw loads
+template <int C>
+__device__ __forceinline__ void pcm_load_frame(const int16_t* __restrict__ pa, const int16_t* __restrict__ pb,
+                                               const int16_t* __restrict__ pb0, bool live_a0, bool live_b0, float scale,
+                                               float4* xa, float4* xb) {
+    constexpr int kBatch = (C == 4) ? 4 : (C == 2 ? 8 : 16);
+    constexpr int rowc = 128 * 16 * C;                                      // 16 rows
+#pragma unroll
+    for (int b0 = 0; b0 < 16; b0 += kBatch) {
+        PcmRaw<C> raw[kBatch];
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+            const int pos = b0 + i, c = pos & 7;
+            if (pos < 8) raw[i] = pcm_load_raw<C>(pa + rowc * c, c > 0 || live_a0);
+            else raw[i] = pcm_load_raw<C>(c == 0 ? pb0 : pb - rowc * c, c > 0 || live_b0);
+        }
+#pragma unroll
+        for (int i = 0; i < kBatch; ++i) {
+            const int pos = b0 + i;
+            if (pos < 8) xa[pos] = pcm_to_mono4<C>(raw[i], scale);
+            else xb[pos - 8] = pcm_to_mono4<C>(raw[i], scale);
+        }
+    }
 }
 
-template <int MODE, int IN>   // MODE 0: log-mel output; 1: complex STFT output.  IN 0: fp32 mono; 1: 16-bit PCM
+constexpr int kInPcmAny = 16;   // IN value: 16-bit PCM with a run-time channel count (scalar loads)
+
+// MODE 0: log-mel output; 1: complex STFT output.  IN 0: fp32 mono; 1, 2, 4: 16-bit PCM with that many interleaved
+// channels (vector loads); kInPcmAny: 16-bit PCM, any channel count.
+template <int MODE, int IN>
 __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelParams prm) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* b2_s = smem + kOffB2;
@@ -519,14 +571,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                     }
                 }
             } else {
-                const int C = prm.n_channels;
+                const int C = (IN == kInPcmAny) ? prm.n_channels : IN;           // compile-time for 1, 2, 4 channels
                 const float ps = prm.pcm_scale;
                 const int16_t* __restrict__ y = prm.pcm + static_cast<long long>(clip) * prm.wave_stride * C;
-                const bool vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && (C == 1 || C == 2 || C == 4);
+                const bool vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && IN != kInPcmAny;
                 auto load4 = [&](int n0) -> float4 {
                     const int j0 = t * kHop + n0 - kPadRefl;
                     if (n0 < kLpad - 3 || n0 >= kLpad + kWin) return make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (vec_ok && j0 >= 0 && j0 + 4 <= L) return pcm_mono4(y + static_cast<long long>(j0) * C, C, ps);
                     float v[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -541,15 +592,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                     const int16_t* fr = y + (static_cast<long long>(t) * kHop - kPadRefl + 4 * lane) * C;
                     const int16_t* pa = fr + 128 * r * C;
                     const int16_t* pb = fr + 128 * (256 - r) * C;
-                    const int rowc = 128 * 16 * C;                                               // 16 rows
-                    xa[0] = (na >= kLpad) ? pcm_mono4(pa, C, ps) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    xb[0] = (nb < kLpad + kWin) ? pcm_mono4(r == 0 ? pb - 128 * 128 * C : pb, C, ps)
-                                                : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int c = 1; c < 8; ++c) {
-                        xa[c] = pcm_mono4(pa + rowc * c, C, ps);
-                        xb[c] = pcm_mono4(pb - rowc * c, C, ps);
-                    }
+                    const int16_t* pb0 = (r == 0) ? pb - 128 * 128 * C : pb;
+                    const bool la = na >= kLpad, lb = nb < kLpad + kWin;
+                    if constexpr (IN == 1 || IN == 2 || IN == 4) pcm_load_frame<IN>(pa, pb, pb0, la, lb, ps, xa, xb);
                 } else {
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {

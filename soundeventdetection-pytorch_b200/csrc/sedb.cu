@@ -129,6 +129,12 @@ int sedb_create(sedb_ctx_t** out_ctx) {
                                   sedb::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(sedb::logmel_fused_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   sedb::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(sedb::logmel_fused_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  sedb::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(sedb::logmel_fused_kernel<0, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  sedb::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(sedb::logmel_fused_kernel<0, sedb::kInPcmAny>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, sedb::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(sedb::logmel_fused_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   sedb::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(sedb::power_mel_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -196,8 +202,14 @@ static int launch_logmel(sedb_ctx_t* c, int mode, const void* wave, long long n_
     const int grid = static_cast<int>(total < c->num_sms ? total : c->num_sms);
     if (mode == 0 && in_fmt == 0)
         sedb::logmel_fused_kernel<0, 0><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
-    else if (mode == 0)
+    else if (mode == 0 && n_channels == 1)
         sedb::logmel_fused_kernel<0, 1><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
+    else if (mode == 0 && n_channels == 2)
+        sedb::logmel_fused_kernel<0, 2><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
+    else if (mode == 0 && n_channels == 4)
+        sedb::logmel_fused_kernel<0, 4><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
+    else if (mode == 0)
+        sedb::logmel_fused_kernel<0, sedb::kInPcmAny><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
     else if (in_fmt == 0)
         sedb::logmel_fused_kernel<1, 0><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
     else

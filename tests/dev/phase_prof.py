@@ -8,6 +8,8 @@ from sed_b200.dataset.spectogram import preprocess as P
 lib = _ext.load()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 64
 w = (torch.randn(B, 2880000, device="cuda") * 0.1).clamp_(-1, 1)
+if len(sys.argv) > 2 and sys.argv[2] == "pcm16":
+    w = (w * 32767.0).round_().to(torch.int16)
 for _ in range(2): P.waveform_to_log_mel(w)
 torch.cuda.synchronize()
 lib.sedb_debug_phase_profile(1, None)
