@@ -190,7 +190,7 @@ def transform(x, mean, std, preprocessed_mode='logMel'):
 
 
 def preprocess_data(audio_path_and_labels, output_dir, output_mean_std_file, preprocess_mode='logMel',
-                    read_audio=None, batch_files=16):
+                    read_audio=None, batch_files=16, pcm16=False):
     """Drop-in for the reference's ``preprocess_data`` (preprocess.py:60-81), batched through the fused kernel.
 
     Writes, per file, ``<audio_name>_<mode>_features_and_labels.pkl`` = ``{'features', 'start_times', 'end_times'}``
@@ -199,10 +199,25 @@ def preprocess_data(audio_path_and_labels, output_dir, output_mean_std_file, pre
     the reference's ``SpectogramDataset`` loads the result unchanged.  ``read_audio(path) -> (samples, channels)``
     defaults to the reference's ``read_multichannel_audio`` (needs ``soundfile``); files of equal length are processed
     ``batch_files`` at a time.  The debug plot of the reference (preprocess.py:83-86) is not produced.
+
+    ``pcm16=True`` (logMel mode, ``audio_channels == 1``): 16-bit PCM WAV files are read as stored
+    (``dataset_utils.read_wav_pcm16``) and go to the device as int16; the ``/ 32768`` scaling and the channel mean of
+    ``read_multichannel_audio`` happen inside the log-mel kernel's loader (half the host->device bytes of float32 mono,
+    an eighth of 4-channel float64).
     """
     import os
     import pickle
 
+    if pcm16:
+        from .. import dataset_utils
+        if preprocess_mode != 'logMel' or cfg.audio_channels != 1:
+            raise ValueError("pcm16=True needs preprocess_mode='logMel' and audio_channels == 1")
+
+        def read_audio(path):                          # noqa: F811 - the int16 reader replaces the float one
+            pcm, rate = dataset_utils.read_wav_pcm16(path)
+            if rate != cfg.working_sample_rate:
+                raise RuntimeError(f"{path}: sample rate {rate} != {cfg.working_sample_rate}; resample first")
+            return pcm
     if read_audio is None:
         try:
             import soundfile  # noqa: F401
@@ -219,6 +234,18 @@ def preprocess_data(audio_path_and_labels, output_dir, output_mean_std_file, pre
     def flush(group):
         nonlocal s1, s2, s1c, count
         waves = [g[0] for g in group]
+        if pcm16:
+            feats = pcm16_to_log_mel(torch.from_numpy(np.ascontiguousarray(np.stack(waves))).cuda())
+            f64 = feats.to(torch.float64)
+            s1 += f64.sum((0, 1))
+            s2 += (f64 * f64).sum((0, 1))
+            count += feats.shape[0] * feats.shape[1]
+            feats = feats[:, None].cpu().numpy()                   # (files, 1, T, 64)
+            for (wave, start_times, end_times, audio_name), feature in zip(group, feats):
+                path = os.path.join(output_dir, audio_name + f"_{preprocess_mode}_features_and_labels.pkl")
+                with open(path, 'wb') as fh:
+                    pickle.dump({'features': feature, 'start_times': start_times, 'end_times': end_times}, fh)
+            return
         C = waves[0].shape[1]
         stacked = torch.from_numpy(np.ascontiguousarray(np.stack([w.T for w in waves]), dtype=np.float32)).cuda()
         flat = stacked.reshape(len(waves) * C, -1)                   # one mono "clip" per (file, channel)

@@ -49,3 +49,35 @@ def test_transform_logmel_and_complex_modes():
     assert out_c.shape == ref.shape and np.abs(out_c - ref).max() < 1e-2
     with pytest.raises(ValueError):
         P.transform(lm, mean, std, "other")
+
+
+def test_preprocess_data_from_pcm16_wav_files(tmp_path):
+    """The f-3 hand-over: 16-bit PCM WAV files (4-channel, TAU-FOA-like) -> int16 batches -> channel mean and scaling
+    inside the kernel loader; pickles and statistics equal the reference reader + reference log-mel."""
+    import wave
+    from oracle import audio_ref as A
+    rng = np.random.default_rng(3)
+    items, pcms = [], {}
+    for i in range(3):
+        n = 110880
+        base = signals.hdr(n, 70 + i)
+        pcm = np.stack([np.clip(np.round((0.2 + 0.1 * c) * base * 32768 + 20 * rng.standard_normal(n)), -32768, 32767)
+                        for c in range(4)], axis=1).astype(np.int16)
+        path = str(tmp_path / f"foa{i}.wav")
+        with wave.open(path, "wb") as w:
+            w.setnchannels(4); w.setsampwidth(2); w.setframerate(48000); w.writeframes(pcm.tobytes())
+        items.append((path, [0.5], [1.0], f"foa{i}"))
+        pcms[f"foa{i}"] = pcm
+    out_dir, stats = str(tmp_path / "feat"), str(tmp_path / "mean_std.pkl")
+    mean, std = P.preprocess_data(items, out_dir, stats, preprocess_mode="logMel", pcm16=True, batch_files=2)
+    refs = []
+    for name, pcm in pcms.items():
+        d = pickle.load(open(os.path.join(out_dir, name + "_logMel_features_and_labels.pkl"), "rb"))
+        ref = R.waveform_to_log_mel(A.pcm16_to_mono(pcm))[None]
+        assert d["features"].shape == ref.shape == (1, 8, 64) and d["features"].dtype == np.float32
+        assert np.abs(d["features"] - ref).max() < 1e-2
+        refs.append(ref)
+    ref_mean, ref_std = R.calculate_scalar_of_tensor(np.concatenate(refs, axis=1))
+    assert np.abs(mean - ref_mean).max() < 1e-2 and np.abs(std - ref_std).max() < 1e-2
+    with pytest.raises(ValueError):
+        P.preprocess_data(items, out_dir, stats, preprocess_mode="Complex", pcm16=True)
