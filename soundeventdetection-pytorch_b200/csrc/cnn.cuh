@@ -31,7 +31,8 @@ namespace sedb {
 constexpr int kConvThreads = 320;          // 8 epilogue warps + MMA warp + copy warp
 constexpr int kConvMaxTiles = 4;            // M tiles (128 pixels) per work item
 constexpr int kConvMaxWSlots = 6;
-constexpr int kConvMaxWSlotBytes = 16384;  // weight ring slot: `kpb` consecutive (tap, 16-channel) blocks of hi|lo x [cout_tile][16]
+constexpr int kConvMaxWSlotBytes = 16384;  // weight ring slot: `kpb` consecutive taps of one 16-channel K-step, hi|lo x [cout_tile][16] each
+constexpr int kConvMaxKSteps = 8;          // 16-channel K-steps per input-channel chunk (cin_chunk <= 128)
 constexpr int kConvLead = 8;
 
 struct ConvParams {
@@ -53,7 +54,7 @@ struct ConvParams {
     int tapoff[9];           // tap offsets in pixels relative to the patch start
     int patch_bytes;         // 2 * (cin_chunk/8) * P * 16
     int n_wslots;            // weight ring slots (<= kConvMaxWSlots)
-    int kpb;                 // 16-channel K-steps per weight ring slot (divides cin_chunk/16)
+    int kpb;                 // taps per weight ring slot (divides ntaps)
     int wslot_bytes;         // kpb * cout_tile * 64
     int stage_bytes;         // pooling stage (0 without pooling)
     unsigned long long* prof; // nullable diagnostics: [0] epilogue wait, [1] epilogue work, [2] mma wait patch,
@@ -90,14 +91,17 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
     float* sh_s = sc_s + p.cout;
     uint64_t* bars = reinterpret_cast<uint64_t*>(
         (reinterpret_cast<uintptr_t>(sh_s + p.cout) + 15) & ~static_cast<uintptr_t>(15));
-    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 24);
+    uint32_t* tmem_ptr_s = reinterpret_cast<uint32_t*>(bars + 32);
 
+    // The patch is filled and released per 16-channel K-step (the MMA loop is K-step major, taps inner): as soon as
+    // the MMAs of a K-step are done its two K-groups are reloaded for the next work item, so the patch transfer of
+    // item t+1 overlaps the remaining MMAs of item t instead of being exposed between items.
     uint64_t* wfull = bars + 0;        // [6]
     uint64_t* wempty = bars + 6;       // [6]
-    uint64_t* patch_full = bars + 12;
-    uint64_t* patch_free = bars + 13;
-    uint64_t* acc_full = bars + 14;    // [2]
-    uint64_t* epi_done = bars + 16;    // [2]
+    uint64_t* patch_full = bars + 12;  // [8] per K-step
+    uint64_t* patch_free = bars + 20;  // [8] per K-step
+    uint64_t* acc_full = bars + 28;    // [2]
+    uint64_t* epi_done = bars + 30;    // [2]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid == 0) {
@@ -105,8 +109,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
             mbar_init(&wfull[s], 1);
             mbar_init(&wempty[s], 1);
         }
-        mbar_init(patch_full, 1);
-        mbar_init(patch_free, 1);
+        for (int s = 0; s < kConvMaxKSteps; ++s) {
+            mbar_init(&patch_full[s], 1);
+            mbar_init(&patch_free[s], 1);
+        }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
             mbar_init(&epi_done[s], 8);
@@ -132,6 +138,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
     const int ks_chunk = p.cin_chunk / 16;
     const int wblock_bytes = p.cout_tile * 64;
     const int blocks_per_kc = p.ntaps * ks_chunk;
+    const int group_bytes = p.kpb * wblock_bytes;
 
     auto decode = [&](int it, int& img, int& band, int& ntile) {
         int item = blockIdx.x + it * gridDim.x;
@@ -154,31 +161,33 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                 const int v0 = band_v0(band);
                 for (int kc = 0; kc < p.n_kchunks; ++kc) {
                     const int gk = it * p.n_kchunks + kc;
-                    tprev = clock64();
-                    if (gk > 0) mbar_wait(patch_free, (gk - 1) & 1);
-                    CONV_PROF(5);
-                    if (elect_one()) {
-                        mbar_arrive_expect_tx(patch_full, p.patch_bytes);
-                        for (int arr = 0; arr < 2; ++arr)
-                            for (int kgl = 0; kgl < kg_chunk; ++kgl) {
-                                const long long plane =
-                                    (static_cast<long long>(img) * 2 + arr) * (p.cin / 8) + kc * kg_chunk + kgl;
-                                const uint8_t* src = p.in + (plane * p.S_in + kConvLead + v0 - p.halo) * 16;
-                                bulk_g2s(patch + (arr * kg_chunk + kgl) * p.P * 16, src, p.P * 16, patch_full);
-                            }
-                    }
-                    __syncwarp();
                     const uint8_t* wsrc = p.wpack + static_cast<long long>(ntile * p.n_kchunks + kc) * blocks_per_kc * wblock_bytes;
-                    const int group_bytes = p.kpb * wblock_bytes;
-                    for (int b = 0; b < blocks_per_kc; b += p.kpb, ++gw) {
-                        const int s = gw % p.n_wslots, u = gw / p.n_wslots;
-                        mbar_wait(&wempty[s], (u & 1) ^ 1);
+                    for (int ks = 0; ks < ks_chunk; ++ks) {
+                        tprev = clock64();
+                        if (gk > 0) mbar_wait(&patch_free[ks], (gk - 1) & 1);
+                        CONV_PROF(5);
                         if (elect_one()) {
-                            mbar_arrive_expect_tx(&wfull[s], group_bytes);
-                            bulk_g2s(wring + s * p.wslot_bytes, wsrc + static_cast<long long>(b) * wblock_bytes,
-                                     group_bytes, &wfull[s]);
+                            mbar_arrive_expect_tx(&patch_full[ks], 4 * p.P * 16);
+                            for (int arr = 0; arr < 2; ++arr)
+                                for (int h = 0; h < 2; ++h) {
+                                    const int kgl = 2 * ks + h;
+                                    const long long plane =
+                                        (static_cast<long long>(img) * 2 + arr) * (p.cin / 8) + kc * kg_chunk + kgl;
+                                    const uint8_t* src = p.in + (plane * p.S_in + kConvLead + v0 - p.halo) * 16;
+                                    bulk_g2s(patch + (arr * kg_chunk + kgl) * p.P * 16, src, p.P * 16, &patch_full[ks]);
+                                }
                         }
                         __syncwarp();
+                        for (int b = 0; b < p.ntaps; b += p.kpb, ++gw) {
+                            const int s = gw % p.n_wslots, u = gw / p.n_wslots;
+                            mbar_wait(&wempty[s], (u & 1) ^ 1);
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(&wfull[s], group_bytes);
+                                bulk_g2s(wring + s * p.wslot_bytes,
+                                         wsrc + static_cast<long long>(ks * p.ntaps + b) * wblock_bytes, group_bytes, &wfull[s]);
+                            }
+                            __syncwarp();
+                        }
                     }
                 }
             }
@@ -209,15 +218,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                 CONV_PROF(4);
                 for (int kc = 0; kc < p.n_kchunks; ++kc) {
                     const int gk = it * p.n_kchunks + kc;
-                    mbar_wait(patch_full, gk & 1);
-                    tc_fence_after();
-                    CONV_PROF(2);
                     // Descriptors differ only in their start-address field (16-byte units, low 14 bits), so every
                     // operand is the base descriptor plus an offset: the single issuing thread stays a few
                     // instructions per MMA.
-                    for (int tap = 0; tap < p.ntaps; ++tap) {
-                        const uint32_t tap_off = p.tapoff[tap];
-                        for (int ks0 = 0; ks0 < ks_chunk; ks0 += p.kpb, ++gw) {
+                    for (int ks = 0; ks < ks_chunk; ++ks) {
+                        CONV_PROF(3);                                   // MMA issue (+ weight waits) since the last point
+                        mbar_wait(&patch_full[ks], gk & 1);
+                        tc_fence_after();
+                        CONV_PROF(2);                                   // wait for this K-step's patch groups
+                        const uint32_t ks_off = 2 * ks * p.P;
+                        for (int tap0 = 0; tap0 < p.ntaps; tap0 += p.kpb, ++gw) {
                             const int s = gw % p.n_wslots, u = gw / p.n_wslots;
                             mbar_wait(&wfull[s], u & 1);
                             tc_fence_after();
@@ -225,10 +235,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                                 uint64_t bH = b_base + static_cast<uint32_t>(s * (p.wslot_bytes >> 4));
                                 for (int j = 0; j < p.kpb; ++j) {
                                     const uint64_t bL = bH + b_lo_delta;
-                                    const uint32_t acc = (kc > 0 || tap > 0 || ks0 + j > 0) ? 1u : 0u;
+                                    const uint32_t acc = (kc > 0 || ks > 0 || tap0 + j > 0) ? 1u : 0u;
                                     // tiles unrolled with immediate operand offsets: the single issuing lane must
                                     // not spend more instructions per MMA than a narrow (N = 32) MMA takes to run
-                                    const uint64_t aH = a_base + (2 * (ks0 + j) * p.P + tap_off);
+                                    const uint64_t aH = a_base + (ks_off + p.tapoff[tap0 + j]);
                                     const uint64_t aL = aH + a_lo_delta;
                                     const uint32_t ct = p.cout_tile;
 #pragma unroll
@@ -239,18 +249,19 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                                             umma_f16(acc_base + m * ct, aH + 128 * m, bL, idesc, 1u);
                                         }
                                     }
-                                    bH += 2 * b_lo_delta;            // next 16-channel block of the group
+                                    bH += 2 * b_lo_delta;            // next tap of the group
                                 }
                                 umma_commit(&wempty[s]);
                             }
                             __syncwarp();
                         }
+                        if (elect_one()) umma_commit(&patch_free[ks]);      // this K-step's patch groups may be refilled
+                        __syncwarp();
                     }
-                    if (elect_one()) {
-                        umma_commit(patch_free);
-                        if (kc + 1 == p.n_kchunks) umma_commit(&acc_full[it & 1]);
+                    if (kc + 1 == p.n_kchunks) {
+                        if (elect_one()) umma_commit(&acc_full[it & 1]);
+                        __syncwarp();
                     }
-                    __syncwarp();
                     CONV_PROF(3);
                 }
             }
@@ -727,7 +738,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, uint8_t* __
     const int kc = ci / cin_chunk, cil = ci % cin_chunk;
     const int ks = cil / 16, k = cil % 16;
     const int n_kchunks = cin / cin_chunk, ks_chunk = cin_chunk / 16;
-    const long long block = ((static_cast<long long>(ntile) * n_kchunks + kc) * ntaps + tap) * ks_chunk + ks;
+    const long long block = ((static_cast<long long>(ntile) * n_kchunks + kc) * ks_chunk + ks) * ntaps + tap;   // K-step major
     const long long base = block * (cout_tile * 64);
     const int off = (k / 8) * (cout_tile * 16) + n * 16 + (k % 8) * 2;
     *reinterpret_cast<__nv_bfloat16*>(out + base + off) = h;

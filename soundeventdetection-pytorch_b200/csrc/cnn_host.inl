@@ -85,17 +85,16 @@ int plan_umma_layer_tiles(const UmmaLayer& L, int H, int W, int max_tiles, sedb:
 size_t conv_smem_bytes(const sedb::ConvParams& p) {
     const size_t patch = (static_cast<size_t>(p.patch_bytes) + 127) / 128 * 128;
     return patch + static_cast<size_t>(p.n_wslots) * p.wslot_bytes + p.stage_bytes +
-           static_cast<size_t>(2) * p.cout * 4 + 16 + 24 * 8 + 16 + 128;
+           static_cast<size_t>(2) * p.cout * 4 + 16 + 32 * 8 + 16 + 128;
 }
 
 // Weight-ring geometry and pooling stage next to the patch: prefer several K-steps per slot (fewer barrier round
 // trips for the MMA issuer), then as many slots as fit.
 bool conv_fit_smem(sedb::ConvParams& p) {
     p.stage_bytes = (p.pool != 1) ? 128 * p.n_tiles * 17 * 4 : 0;
-    const int ks_chunk = p.cin_chunk / 16;
     const int wblock = p.cout_tile * 64;
-    for (int kpb = ks_chunk; kpb >= 1; --kpb) {
-        if (ks_chunk % kpb || kpb * wblock > sedb::kConvMaxWSlotBytes) continue;
+    for (int kpb = p.ntaps; kpb >= 1; --kpb) {                 // taps per slot: a divisor of the tap count
+        if (p.ntaps % kpb || kpb * wblock > sedb::kConvMaxWSlotBytes) continue;
         p.kpb = kpb;
         p.wslot_bytes = kpb * wblock;
         for (int slots = sedb::kConvMaxWSlots; slots >= 3; --slots) {
