@@ -31,7 +31,7 @@ namespace sedb {
 constexpr int kConvThreads = 320;          // 8 epilogue warps + MMA warp + copy warp
 constexpr int kConvMaxTiles = 4;            // M tiles (128 pixels) per work item
 constexpr int kConvMaxWSlots = 6;
-constexpr int kConvMaxWSlotBytes = 16384;  // weight ring slot: `kpb` consecutive taps of one 16-channel K-step, hi|lo x [cout_tile][16] each
+constexpr int kConvMaxWSlotBytes = 40960;  // weight ring slot: `kpb` consecutive taps of one 16-channel K-step, hi|lo x [cout_tile][16] each
 constexpr int kConvMaxKSteps = 8;          // 16-channel K-steps per input-channel chunk (cin_chunk <= 128)
 constexpr int kConvLead = 8;
 

@@ -97,7 +97,7 @@ bool conv_fit_smem(sedb::ConvParams& p) {
         if (p.ntaps % kpb || kpb * wblock > sedb::kConvMaxWSlotBytes) continue;
         p.kpb = kpb;
         p.wslot_bytes = kpb * wblock;
-        for (int slots = sedb::kConvMaxWSlots; slots >= 3; --slots) {
+        for (int slots = sedb::kConvMaxWSlots; slots >= 2; --slots) {
             p.n_wslots = slots;
             if (conv_smem_bytes(p) <= 227 * 1024) return true;
         }
