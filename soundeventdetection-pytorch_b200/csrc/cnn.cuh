@@ -55,6 +55,8 @@ struct ConvParams {
     int patch_bytes;         // 2 * (cin_chunk/8) * P * 16
     int n_wslots;            // weight ring slots (<= kConvMaxWSlots)
     int kpb;                 // taps per weight ring slot (divides ntaps)
+    int ncat;                // 1: weight block rows are [hi | lo] stacked along N (narrow layers, cout_tile = 32): one
+                             //    N = 2 cout_tile MMA gives aH bH and aH bL, so the A tile is read twice instead of 3 times
     int wslot_bytes;         // kpb * cout_tile * 64
     int stage_bytes;         // pooling stage (0 without pooling)
     unsigned long long* prof; // nullable diagnostics: [0] epilogue wait, [1] epilogue work, [2] mma wait patch,
@@ -198,14 +200,16 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
         if (tmem != 0) __trap();
         {
             const uint32_t idesc = make_idesc(kFmtBF16, kMajorK, kMajorK, 128, p.cout_tile);
+            const uint32_t idesc_cat = make_idesc(kFmtBF16, kMajorK, kMajorK, 128, 2 * p.cout_tile);
             const uint32_t patch_a = smem_u32(patch);
             const uint32_t wring_a = smem_u32(wring);
             const uint32_t a_lbo = p.P * 16;
-            const uint32_t b_lbo = p.cout_tile * 16;
+            const uint32_t b_lbo = p.cout_tile * 16 * (p.ncat ? 2 : 1);
             const uint64_t a_base = make_smem_desc(patch_a, a_lbo, 128);
             const uint64_t b_base = make_smem_desc(wring_a, b_lbo, 128);
             const uint32_t a_lo_delta = kg_chunk * p.P;            // lo half of the patch, in 16-byte units
-            const uint32_t b_lo_delta = p.cout_tile * 2;           // lo half of a weight block
+            const uint32_t b_lo_delta = p.cout_tile * 2;           // lo half of a weight block (separate-halves layout)
+            const uint32_t b_block = p.cout_tile * 4;              // one (tap, K-step) block, in 16-byte units
             int gw = 0;
             long long tprev = clock64();
             for (int it = 0; it < n_items; ++it) {
@@ -240,16 +244,26 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                                     // not spend more instructions per MMA than a narrow (N = 32) MMA takes to run
                                     const uint64_t aH = a_base + (ks_off + p.tapoff[tap0 + j]);
                                     const uint64_t aL = aH + a_lo_delta;
-                                    const uint32_t ct = p.cout_tile;
+                                    const uint32_t ct = p.cout_tile * (p.ncat ? 2 : 1);    // accumulator columns per tile
+                                    if (p.ncat) {
 #pragma unroll
-                                    for (int m = 0; m < kConvMaxTiles; ++m) {
-                                        if (m < p.n_tiles) {
-                                            umma_f16(acc_base + m * ct, aH + 128 * m, bH, idesc, acc);
-                                            umma_f16(acc_base + m * ct, aL + 128 * m, bH, idesc, 1u);
-                                            umma_f16(acc_base + m * ct, aH + 128 * m, bL, idesc, 1u);
+                                        for (int m = 0; m < kConvMaxTiles; ++m) {
+                                            if (m < p.n_tiles) {
+                                                umma_f16(acc_base + m * ct, aH + 128 * m, bH, idesc_cat, acc);   // aH [bH | bL]
+                                                umma_f16(acc_base + m * ct, aL + 128 * m, bH, idesc, 1u);        // aL bH
+                                            }
+                                        }
+                                    } else {
+#pragma unroll
+                                        for (int m = 0; m < kConvMaxTiles; ++m) {
+                                            if (m < p.n_tiles) {
+                                                umma_f16(acc_base + m * ct, aH + 128 * m, bH, idesc, acc);
+                                                umma_f16(acc_base + m * ct, aL + 128 * m, bH, idesc, 1u);
+                                                umma_f16(acc_base + m * ct, aH + 128 * m, bL, idesc, 1u);
+                                            }
                                         }
                                     }
-                                    bH += 2 * b_lo_delta;            // next tap of the group
+                                    bH += b_block;                   // next tap of the group
                                 }
                                 umma_commit(&wempty[s]);
                             }
@@ -289,6 +303,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
             tc_fence_after();
             if (tid == 0) { CONV_PROF(0); }
             const uint32_t tacc = tlane + 256 * (it & 1);
+            const int tile_cols = p.cout_tile * (p.ncat ? 2 : 1);
             const long long out_img = static_cast<long long>(img) * 2 * (p.cout / 8);
             if (p.pool == 1) {
                 for (int m = grp; m < p.n_tiles; m += 2) {
@@ -301,7 +316,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                     const long long vout = kConvLead + v0 + pp;
                     for (int c0 = 0; c0 < p.cout_tile; c0 += 16) {
                         float acc[16];
-                        tmem_ld16(tacc + m * p.cout_tile + c0, acc);
+                        tmem_ld16(tacc + m * tile_cols + c0, acc);
+                        if (p.ncat) {                             // add the aH bL half
+                            float acc2[16];
+                            tmem_ld16(tacc + m * tile_cols + p.cout_tile + c0, acc2);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) acc[i] += acc2[i];
+                        }
                         tmem_ld_wait();
                         if (valid) {
 #pragma unroll
@@ -323,7 +345,14 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                     for (int m = grp; m < p.n_tiles; m += 2) {
                         const int pp = 128 * m + 32 * q + lane;
                         float acc[16];
-                        tmem_ld16(tacc + m * p.cout_tile + c0, acc);
+                        tmem_ld16(tacc + m * tile_cols + c0, acc);
+                        if (p.ncat) {
+                            float acc2[16];
+                            tmem_ld16(tacc + m * tile_cols + p.cout_tile + c0, acc2);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) acc[i] += acc2[i];
+                        }
                         tmem_ld_wait();
 #pragma unroll
                         for (int i = 0; i < 16; ++i)
@@ -724,7 +753,7 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
 
 // Conv weight [cout][cin][ntaps] fp32 -> blocks [ntile][kc][tap][ks] of {hi,lo} x canonical K-major [cout_tile][16]
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int cout, int cin,
-                                        int ntaps, int cout_tile, int cin_chunk) {
+                                        int ntaps, int cout_tile, int cin_chunk, int ncat) {
     const long long total = static_cast<long long>(cout) * cin * ntaps;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= total) return;
@@ -740,6 +769,12 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, uint8_t* __
     const int n_kchunks = cin / cin_chunk, ks_chunk = cin_chunk / 16;
     const long long block = ((static_cast<long long>(ntile) * n_kchunks + kc) * ks_chunk + ks) * ntaps + tap;   // K-step major
     const long long base = block * (cout_tile * 64);
+    if (ncat) {      // rows [hi | lo] stacked along N inside each K-group: one N = 2 cout_tile operand
+        const int off = (k / 8) * (cout_tile * 32) + n * 16 + (k % 8) * 2;
+        *reinterpret_cast<__nv_bfloat16*>(out + base + off) = h;
+        *reinterpret_cast<__nv_bfloat16*>(out + base + cout_tile * 16 + off) = l;
+        return;
+    }
     const int off = (k / 8) * (cout_tile * 16) + n * 16 + (k % 8) * 2;
     *reinterpret_cast<__nv_bfloat16*>(out + base + off) = h;
     *reinterpret_cast<__nv_bfloat16*>(out + base + cout_tile * 32 + off) = l;

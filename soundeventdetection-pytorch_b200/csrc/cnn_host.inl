@@ -15,6 +15,7 @@ struct UmmaLayer {          // a conv layer executed by conv_umma_kernel
     float* scale = nullptr;
     float* shift = nullptr;
     int cin_chunk = 0, cout_tile = 0;
+    int ncat = 0;             // weight halves stacked along N (see ConvParams::ncat)
 };
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
@@ -37,8 +38,10 @@ int plan_umma_layer(const UmmaLayer& L, int H, int W, sedb::ConvParams& p) {
     p.n_ntiles = L.cout / L.cout_tile;
     p.pool = L.pool;
     p.ntaps = L.ntaps;
+    p.ncat = L.ncat;
     int max_tiles = (L.cin_chunk <= 64) ? sedb::kConvMaxTiles : 2;
-    if (max_tiles * L.cout_tile > 256) max_tiles = 256 / L.cout_tile;   // accumulators are double buffered in TMEM
+    const int tile_cols = L.cout_tile * (L.ncat ? 2 : 1);
+    if (max_tiles * tile_cols > 256) max_tiles = 256 / tile_cols;       // accumulators are double buffered in TMEM
     return plan_umma_layer_tiles(L, H, W, max_tiles, p);
 }
 
@@ -115,6 +118,7 @@ int final_plane_S(int mode, int H, int W) {
 int alloc_layer_params(UmmaLayer& L) {
     L.cin_chunk = L.cin > 128 ? 128 : L.cin;
     L.cout_tile = L.cout > 128 ? 128 : L.cout;
+    L.ncat = (L.cout_tile == 32 && L.mode == 0) ? 1 : 0;
     if (L.cin % 16 || L.cin % L.cin_chunk || L.cout % 16 || L.cout % L.cout_tile)
         return fail("conv layer %d->%d: channel counts must be multiples of 16 (and of 128 above 128)", L.cin, L.cout);
     CUDA_TRY(cudaMalloc(&L.wpack, static_cast<size_t>(L.cout) * L.cin * L.ntaps * 4));
@@ -156,7 +160,7 @@ int fold_and_pack(UmmaLayer& L, const float* w, const float* bias, const float* 
                   const float* mean, const float* var, cudaStream_t st) {
     const long long total = static_cast<long long>(L.cout) * L.cin * L.ntaps;
     sedb::pack_conv_weight_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(w, L.wpack, L.cout, L.cin,
-                                                                                      L.ntaps, L.cout_tile, L.cin_chunk);
+                                                                                      L.ntaps, L.cout_tile, L.cin_chunk, L.ncat);
     sedb::bn_fold_kernel<<<(L.cout + 127) / 128, 128, 0, st>>>(gamma, beta, mean, var, bias, 1e-5f, L.cout, L.scale,
                                                               L.shift);
     g_launches.fetch_add(2);
