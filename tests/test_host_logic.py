@@ -111,3 +111,23 @@ def test_shard_range_partitions_exactly(n, world):
         assert b0 == a1 and a0 <= b0
     sizes = [b - a for a, b in spans]
     assert max(sizes) - min(sizes) <= 1
+
+
+def test_metric_utils_identical_to_reference_outputs():
+    """The package's calculate_metrics / f_score reproduce the verbatim reference outputs bit for bit."""
+    import os
+    import torch
+    from sed_b200.utils import metric_utils as M
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "metrics_reference.npz"))
+    i = 0
+    while f"probs{i}" in g:
+        r, p, ap = M.calculate_metrics(g[f"probs{i}"], g[f"target{i}"])
+        assert np.array_equal(r, g[f"recall{i}"]) and np.array_equal(p, g[f"precision{i}"]) and ap == g[f"ap{i}"]
+        assert np.array_equal(M.f_score(r, p), g[f"f1_{i}"])
+        r2, p2, ap2 = M.calculate_metrics(torch.from_numpy(g[f"probs{i}"]), torch.from_numpy(g[f"target{i}"]))
+        assert np.array_equal(r, r2) and np.array_equal(p, p2) and ap == ap2
+        i += 1
+    assert i >= 2
+    # empty denominators: recall 1 without events, precision 1 without detections
+    r, p, ap = M.calculate_metrics(np.zeros((8, 1), np.float32), np.zeros((10, 1)))
+    assert np.all(r == 1) and np.all(p == 1) and ap == 0
