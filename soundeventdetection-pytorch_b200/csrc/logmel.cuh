@@ -81,7 +81,7 @@ constexpr int kMmaWarp = 16;
 constexpr int kCopyWarp = 17;
 constexpr int kThreads = 640;                // 16 workers + MMA + copy + 2 idle warps (register allocation is per 4 warps anyway)
 constexpr int kWorkerRegs = 112;             // setmaxnreg: the service warp group gives its registers to the workers
-constexpr int kServiceRegs = 24;
+constexpr int kServiceRegs = 32;              // (4 x 32 + 16 x 112) x 32 = the 96 x 640 registers of the launch
 
 struct LogmelParams {
     const float* wave;        // IN 0: [B, wave_stride] fp32 mono
@@ -327,6 +327,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
     uint64_t* d1_full = bars + 12;   // stage-1 accumulators complete
     uint64_t* d2_full = bars + 13;   // stage-2 accumulators complete
     uint64_t* b2_full = bars + 15;   // resident stage-2 constants landed
+    // log-mel mode: the two helper warps take the mel finalize off the workers
+    uint64_t* part_full = bars + 17; // mel partial moments (and the frame's scale) are in shared memory (16 worker warps)
+    uint64_t* part_free = bars + 18; // helpers have finished the previous frame's finalize
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -341,6 +344,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         mbar_init(d1_full, 1);
         mbar_init(d2_full, 1);
         mbar_init(b2_full, 1);
+        mbar_init(part_full, kWorkerWarps);
+        mbar_init(part_free, 2);
         mbar_fence_init();
     }
     if (warp == kMmaWarp) tmem_alloc<512>(tmem_ptr_s);
@@ -377,6 +382,24 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
     // (issued at the top of each role's own branch: ptxas allocates per region between setmaxnreg and the join)
     if (warp >= kWorkerWarps + 2) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kServiceRegs));
+        // ==================================================================== helper warps (log-mel mode): the mel
+        // finalize of every frame (partial moments of the workers -> 64 filters -> dB -> store) runs here, off the
+        // workers' critical path: 8 passes of 8 filters x 8 lanes.
+        if (MODE == 0) {
+            const int hid = tid - (kWorkerWarps + 2) * 32;            // 0..63
+            for (int it = 0; it < n_iter; ++it) {
+                mbar_wait(part_full, it & 1);
+                const long long f = blockIdx.x + static_cast<long long>(it) * gridDim.x;
+                float* out_row = prm.out + f * kMel;                  // (clip * T + t) * 64 = f * 64
+                const float inv_scale2 = red_s[20];
+#pragma unroll 1
+                for (int pass = 0; pass < 8; ++pass)
+                    mel_finalize<8>(part_s, mel_tab_s, coef_s, prm.norm != nullptr ? norm_s : nullptr, inv_scale2, out_row,
+                                    pass * 64 + hid);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(part_free);
+            }
+        }
     } else if (warp == kCopyWarp) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kServiceRegs));
         if (elect_one()) {
@@ -834,14 +857,13 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 if (tid < 3) p_s[kBins + tid] = 0.f;                  // padding read by the vectorised mel bands
                 worker_sync();                                        // power spectrum complete
                 SEDB_PROF(8);
+                if (it > 0) mbar_wait(part_free, (it - 1) & 1);       // previous frame's finalize has read its moments
                 mel_partials(p_s, mel_tab_s, part_s, tid, kWorkerThreads);
+                if (tid == 0) red_s[20] = inv_scale * inv_scale;      // the frame's block scale, for the finalize
                 SEDB_PROF(9);
-                worker_sync();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(part_full);                // finalize, dB and the store run on the helper warps
                 SEDB_PROF(10);
-                float* out_row = prm.out + (static_cast<long long>(clip) * prm.n_frames + t) * kMel;
-                mel_finalize<kWorkerThreads / kMel>(part_s, mel_tab_s, coef_s, prm.norm != nullptr ? norm_s : nullptr,
-                                                    inv_scale * inv_scale, out_row, tid);
-                SEDB_PROF(11);
             }
             if (MODE != 0) {
                 worker_sync();                                        // stores of this frame done
