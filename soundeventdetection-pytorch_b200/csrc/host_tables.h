@@ -2,6 +2,7 @@
 // canonical shared-memory layout, and the Slaney mel filterbank of the reference
 // (librosa.filters.mel as called at dataset/spectogram/preprocess.py:13-18).
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <cstring>
@@ -168,12 +169,12 @@ struct MelTabEntry {
     int x, y, z, w;
 };
 constexpr int kMelSegments = 65;
-constexpr int kMelPieceLen = 35;      // bins per piece: odd, so consecutive lanes start on distinct banks; <= 512 pieces
+constexpr int kMelPieceLen = 43;      // bins per piece (global grid): odd, so the grid starts cycle through all banks; <= 512 pieces
 constexpr int kMelMaxPieces = 576;
 constexpr int kMelTabEntries = kMelMaxPieces / 2 + 80;      // int4 entries: 2 pieces each, then 65 segment ranges
 
-// One piece per thread: tab[i/2].{x,y} or .{z,w} = {first bin | length << 16, first bin of the segment}; a piece's
-// partial moments go to slot i.  tab[kMelMaxPieces/2 + s] = {first piece, number of pieces, 0, 0} of segment s.
+// One piece per thread position i: tab[i/2].{x,y} or .{z,w} = {first bin | length << 16, first bin of the segment |
+// slot << 16} (length 0: unused position); a piece's partial moments go to its slot (pieces are numbered in segment order).  tab[kMelMaxPieces/2 + s] = {first piece, number of pieces, 0, 0} of segment s.
 // coef[4 m .. +3] = {ar, br, af, bf} of filter m (br, bf already expressed in segment-local bin coordinates).
 inline bool make_mel_moment_tables(int sr, int n_fft, int n_mels, double fmin, double fmax,
                                    std::vector<MelTabEntry>& tab, std::vector<float>& coef, int& n_pieces) {
@@ -203,18 +204,55 @@ inline bool make_mel_moment_tables(int sr, int n_fft, int n_mels, double fmin, d
         coef[4 * m + 3] = static_cast<float>(af * kb[m + 1] + bf);
     }
     tab.assign(kMelTabEntries, MelTabEntry{0, 0, 0, 0});
+    struct Piece { int k, len, seg_first_bin, slot; };
+    std::vector<Piece> pieces;
     int piece = 0;
     for (int s = 0; s < kMelSegments; ++s) {
         const int first_piece = piece;
-        for (int k = kb[s]; k < kb[s + 1]; k += kMelPieceLen) {
+        // pieces are cut on a global grid of kMelPieceLen bins (and at the segment ends): the grid starts cycle evenly
+        // through the 32 banks, only the 65 segment starts fall where they fall
+        for (int k = kb[s]; k < kb[s + 1];) {
             if (piece >= kMelMaxPieces) return false;
-            const int len = (kb[s + 1] - k < kMelPieceLen) ? kb[s + 1] - k : kMelPieceLen;
-            MelTabEntry& e = tab[piece / 2];
-            if (piece & 1) { e.z = k | (len << 16); e.w = kb[s]; }
-            else           { e.x = k | (len << 16); e.y = kb[s]; }
+            int end = (k / kMelPieceLen + 1) * kMelPieceLen;
+            if (end > kb[s + 1]) end = kb[s + 1];
+            pieces.push_back(Piece{k, end - k, kb[s], piece});
             ++piece;
+            k = end;
         }
         tab[kMelMaxPieces / 2 + s] = MelTabEntry{first_piece, piece - first_piece, 0, 0};
+    }
+    // Thread positions: the 32 pieces a warp walks in lock step should start on 32 different shared-memory banks
+    // (first bin mod 32 all distinct), which the segment boundaries spoil in segment order.  Greedy fill: every warp takes
+    // one piece of each residue class while the class lasts; what is left over goes to the free lanes.
+    std::vector<std::vector<Piece>> by_res(32);
+    for (const Piece& q : pieces) by_res[q.k & 31].push_back(q);
+    std::vector<Piece> order(kMelMaxPieces, Piece{0, 0, 0, 0});
+    const int n_warps = piece <= 512 ? 16 : (piece + 31) / 32; // one pass of a 512-thread CTA, with slack lanes if possible
+    std::vector<int> load(n_warps, 0);
+    std::vector<std::vector<int>> res_cnt(n_warps, std::vector<int>(32, 0));
+    std::vector<int> cls(32);
+    for (int r = 0; r < 32; ++r) cls[r] = r;
+    std::sort(cls.begin(), cls.end(), [&](int a, int b) { return by_res[a].size() > by_res[b].size(); });
+    for (int r : cls)                                          // big classes first; each piece to the warp that has the
+        for (const Piece& q : by_res[r]) {                     // fewest pieces of its class, then the fewest pieces
+            int best = -1;
+            for (int w = 0; w < n_warps; ++w) {
+                if (load[w] >= 32) continue;
+                if (best < 0 || res_cnt[w][r] < res_cnt[best][r] ||
+                    (res_cnt[w][r] == res_cnt[best][r] && load[w] < load[best]))
+                    best = w;
+            }
+            if (best < 0) return false;
+            order[best * 32 + load[best]] = q;
+            ++load[best];
+            ++res_cnt[best][r];
+        }
+    for (int i = 0; i < kMelMaxPieces; ++i) {
+        const Piece& q = order[i];
+        MelTabEntry& e = tab[i / 2];
+        const int a = q.k | (q.len << 16), b = q.seg_first_bin | (q.slot << 16);
+        if (i & 1) { e.z = a; e.w = b; }
+        else       { e.x = a; e.y = b; }
     }
     n_pieces = piece;
     return true;

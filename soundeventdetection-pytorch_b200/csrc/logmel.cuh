@@ -60,6 +60,7 @@ constexpr int kOffX128 = kOffAlt + 16 * 128 * 4;           // X[128, n2]      12
 constexpr int kOffV = kOffX128 + 512;                      // Y[n2,128]       128 floats
 constexpr int kOffCs = kOffV + 512;                        // exp(-2 pi i j/256) 256 float2
 constexpr int kMelMaxPieces = 576;                         // host_tables.h: make_mel_moment_tables
+constexpr int kMelPieceLen = 43;                           // host_tables.h: longest piece (checked in sedb.cu)
 constexpr int kMelTabEntries = kMelMaxPieces / 2 + 80;
 constexpr int kOffMelTab = kOffCs + 2048;                  // segment table (320 x int4)
 constexpr int kOffMelPart = kOffMelTab + kMelTabEntries * 16;   // partial moments (2 x kMelMaxPieces floats)
@@ -173,17 +174,28 @@ __device__ __forceinline__ void mel_partials(const float* __restrict__ p_s, cons
     for (int i = idx; i < kMelMaxPieces; i += nthreads) {
         const int2 e = pieces[i];
         const int k0 = e.x & 0xffff, len = e.x >> 16;
+        if (len == 0) continue;                                      // unused thread position
+        const int slot = e.y >> 16;
         const float* p = p_s + k0;
-        float s0 = 0.f, s1 = 0.f, kf = static_cast<float>(k0 - e.y);
-#pragma unroll 4
-        for (int j = 0; j < len; ++j) {
-            const float v = p[j];
-            s0 += v;
-            s1 = fmaf(kf, v, s1);
-            kf += 1.0f;
+        // straight-line over the maximum piece length (bins past the piece are read and discarded: they are still inside
+        // the spectrum's buffer), so that all loads are in flight before the first add waits; two accumulator pairs;
+        // sum (k - kb) P = (k0 - kb) sum P + sum j P with compile-time j
+        const float kf0 = static_cast<float>(k0 - (e.y & 0xffff));
+        float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < kMelPieceLen; j += 2) {
+            const float v0 = (j < len) ? p[j] : 0.f;
+            a0 += v0;
+            b0 = fmaf(static_cast<float>(j), v0, b0);
+            if (j + 1 < kMelPieceLen) {
+                const float v1 = (j + 1 < len) ? p[j + 1] : 0.f;
+                a1 += v1;
+                b1 = fmaf(static_cast<float>(j + 1), v1, b1);
+            }
         }
-        part_s[i] = s0;
-        part_s[kMelMaxPieces + i] = s1;
+        const float s0 = a0 + a1;
+        part_s[slot] = s0;
+        part_s[kMelMaxPieces + slot] = fmaf(kf0, s0, b0 + b1);
     }
 }
 // TPF threads per filter (64 * TPF threads in total): thread (m, sub) adds every TPF-th partial slot of segments m and

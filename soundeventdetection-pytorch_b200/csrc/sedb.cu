@@ -64,6 +64,8 @@ struct sedb_ctx {
 };
 
 #include "cnn_host.inl"
+static_assert(sedb::kMelPieceLen == sedb_host::kMelPieceLen && sedb::kMelMaxPieces == sedb_host::kMelMaxPieces,
+              "mel piece geometry: kernels and host tables must agree");
 
 extern "C" {
 
