@@ -10,7 +10,7 @@ rank processes its own C clips (weak scaling, no data-path collective); `value` 
 
 Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   roofline      dominant kernel (logmel_fused_kernel): algorithmic HBM bytes / CUDA-event time vs MEASURED_PEAKS.json
-  tensor        executed tensor-core FLOPs of the same kernel vs the measured bf16 peak (it is tensor-bound in practice)
+  tensor        executed tensor-core FLOPs of the same kernel vs the measured bf16 peak (the MMAs run at their floor; the rest is operand production)
   cpu_baseline  the oracle port of the reference CPU path timed on this box's host cores on a bounded sample
   e2e           same metric through the C-ABI host-buffer entry point (pinned host memory, H2D + D2H inside the timing)
 """
@@ -347,7 +347,7 @@ def run_ours(args):
                      "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": profiled_traffic(C), "peak_source": src,
                      "algorithmic_bytes_per_launch": C * ALGO_BYTES_PER_CLIP, "ms_per_launch": lm_ms},
         "tensor": {"kernel": "logmel_fused_kernel", "executed_tflops": tflops, "peak": tf_peak, "unit": "TFLOP/s",
-                   "frac": tflops / tf_peak, "note": "split-operand DFT GEMMs executed on tcgen05; the MMAs run at their hardware floor (29 % of the frame time), the rest is operand production and the exposed frame load"},
+                   "frac": tflops / tf_peak, "note": "split-operand DFT GEMMs executed on tcgen05; the MMAs run at their hardware floor (about a third of the frame time), the rest is operand production and the exposed frame load"},
         "cnn": {"ms": cnn_ms, "algorithmic_tflops": C * CNN_FLOP_PER_CLIP / (cnn_ms * 1e-3) / 1e12},
         "e2e": {"value": e2e_value, "unit": "audio-hours/sec", "h2d_bytes_per_step": Ce * CLIP_SAMPLES * 4 + 512,
                 "d2h_bytes_per_step": Ce * 176 * 4, "ms_per_step": e2e_ms, "clips_per_step": Ce,
