@@ -77,6 +77,11 @@ class DataParallelTrainer:
         loss = self.criterion(self.model(x), target)
         loss.backward()
         allreduce_sum_(self.flat.grad)
+        self.apply_update()
+        return loss.detach()
+
+    def apply_update(self):
+        """Fused Adam-amsgrad on the flat buffers (gradients already summed over the ranks)."""
         self.step_count += 1
         p = lambda t: ctypes.c_void_p(t.data_ptr())        # noqa: E731
         with torch.cuda.device(self.flat.param.device):
@@ -85,9 +90,12 @@ class DataParallelTrainer:
                 self.flat.numel, self.lr, self.betas[0], self.betas[1], self.eps, self.weight_decay, self.step_count,
                 1.0 / self.world, _ext.stream_ptr()))
         # in-place update of tensors the native inference handle may have packed: bump their version counters
+        bump = getattr(torch.autograd.graph, "increment_version", None)
         for q in self.flat.params:
-            q.data.add_(0)
-        return loss.detach()
+            if bump is not None:
+                bump(q)                                    # no kernel launch
+            else:
+                q.data.add_(0)
 
     def decay_lr(self, factor=0.997):
         """train.py:108-110: lr *= 0.997 every 200 iterations."""

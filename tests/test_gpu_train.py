@@ -77,3 +77,25 @@ def test_weighted_bce_matches_formula():
     o2, t2 = torch.randn(6, 1), (torch.rand(6) > 0.5).float()
     assert torch.allclose(flat(o2, t2), torch.nn.functional.binary_cross_entropy_with_logits(
         o2.reshape(-1), t2, pos_weight=torch.tensor([2.0])))
+
+
+def test_native_handle_sees_fused_updates_without_a_train_forward():
+    """The fused update writes the parameters behind torch's back; the trainer must invalidate the packed weights of
+    the native inference handle (version bump), even when no train-mode forward touched the BatchNorm buffers."""
+    from oracle import cnn_ref
+    torch.manual_seed(3)
+    m, _ = refmodels.seeded_cnn(refmodels.MAIN_CFG)
+    m = m.cuda().eval()
+    trainer = DataParallelTrainer(m, WeightedBCE(recall_factor=5, multi_frame=True), lr=5e-2)
+    x = refmodels.cnn_inputs(30, 77, batch=2).cuda()
+    with torch.no_grad():
+        y0 = m.logits(x).clone()                        # packs the weights
+    g = torch.Generator(device="cuda").manual_seed(5)
+    trainer.flat.grad.copy_(torch.randn(trainer.flat.numel, device="cuda", generator=g))
+    trainer.apply_update()                              # first Adam step: every weight moves by ~lr
+    with torch.no_grad():
+        y1 = m.logits(x)
+    sd = {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    ref = torch.sigmoid(cnn_ref.cnn_avgpooling_forward(sd, x.cpu(), [p for _, p in refmodels.MAIN_CFG]))
+    assert (y1 - y0).abs().max() > 1e-3                 # the update is visible ...
+    assert (y1.cpu() - ref).abs().max() < 1e-3          # ... and it is exactly the updated model
