@@ -93,16 +93,7 @@ inline std::vector<uint8_t> make_stage2_constants(bool fp16) {
     return buf;
 }
 
-// np.hanning(win) centre-padded with zeros to n_fft (librosa util.pad_center), float32.
-inline std::vector<float> make_hann_padded(int win, int n_fft) {
-    std::vector<float> w(n_fft, 0.f);
-    const int lpad = (n_fft - win) / 2;
-    for (int i = 0; i < win; ++i)
-        w[lpad + i] = static_cast<float>(0.5 - 0.5 * std::cos(2.0 * kPi * static_cast<double>(i) / (win - 1)));
-    return w;
-}
-
-// The same window in factored form for the kernel: w[128 m + n2] = sin^2(phi_m + psi_n2) with
+// np.hanning(win) centre-padded with zeros to n_fft (librosa util.pad_center) in factored form: w[128 m + n2] = sin^2(phi_m + psi_n2) with
 // phi_m = pi (128 m - lpad)/(win - 1), psi_n2 = pi n2/(win - 1) (0.5 - 0.5 cos(2x) = sin^2 x; relative accuracy is kept
 // at the window's ends).  Layout: 257 x {sin phi_m, cos phi_m}, then cos psi[128], then sin psi[128].
 inline std::vector<float> make_hann_factors(int win, int n_fft) {

@@ -115,10 +115,6 @@ __device__ __forceinline__ int reflect_index(int j, int n) {
     return j;
 }
 
-__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
-}
-
 // 8 consecutive 32-bit TMEM columns of this warp's 32 lanes
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
     uint32_t r[8];
@@ -136,38 +132,16 @@ __device__ __forceinline__ void tmem_ld2(uint32_t taddr, float* v) {
     v[0] = __uint_as_float(r[0]);
     v[1] = __uint_as_float(r[1]);
 }
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float* v) {
-    uint32_t r[4];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(taddr)
-                 : "memory");
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
-}
 __device__ __forceinline__ void split4(const float2* x, uint2& hi, uint2& lo) {
     split_pack2(x[0], hi.x, lo.x);
     split_pack2(x[1], hi.y, lo.y);
 }
-__device__ __forceinline__ void split4(const float* x, uint2& hi, uint2& lo) {
-    split_pack2(x[0], x[1], hi.x, lo.x);
-    split_pack2(x[2], x[3], hi.y, lo.y);
-}
-
-// split 8 floats into packed hi / lo halves (16 B each)
-__device__ __forceinline__ void split8(const float* x, uint4& hi, uint4& lo) {
-    uint32_t h[4], l[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) split_pack2(x[2 * i], x[2 * i + 1], h[i], l[i]);
-    hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(l[0], l[1], l[2], l[3]);
-}
 
 // Mel filterbank over a power spectrum in shared memory, in moment form (host_tables.h): per segment between two mel
-// points S0 = sum P_k and S1 = sum (k - kb) P_k.  The bins are cut into pieces of <= 35 bins; thread `idx` accumulates
-// pieces idx, idx + nthreads, ... serially (two independent chains, no cross-lane reduction; consecutive lanes start on
-// consecutive banks) and writes the partial moments to the piece's own slot.  The slots of a segment are then added in
-// order by mel_finalize(), so the result does not depend on scheduling.  A block-level barrier goes in between.
+// points S0 = sum P_k and S1 = sum (k - kb) P_k.  The bins are cut into pieces of <= kMelPieceLen bins; thread `idx`
+// accumulates the pieces at table positions idx, idx + nthreads, ... (no cross-lane reduction; the positions of a warp
+// start on different banks where the host table could arrange it) and writes the partial moments to the piece's slot.
+// The slots of a segment are then added in order by mel_finalize(), so the result does not depend on scheduling.
 __device__ __forceinline__ void mel_partials(const float* __restrict__ p_s, const int4* __restrict__ tab_s,
                                              float* __restrict__ part_s, int idx, int nthreads) {
     const int2* pieces = reinterpret_cast<const int2*>(tab_s);
