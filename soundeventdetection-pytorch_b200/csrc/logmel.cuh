@@ -13,9 +13,13 @@
 //   twiddle  CUDA  Z = (Dc + (-1)^k1 X[128] + i Ds) exp(-2 pi i k1 n2/32768)
 //   radix-2  CUDA  E[n] = Z[n] + Z[n+64],  O[n] = (Z[n] - Z[n+64]) exp(-2 pi i n/128)      n in [0,64)
 //   stage 2  GEMM  X[k1 + 256 (2j)]   = sum_n E[k1,n] exp(-2 pi i n j/64)
-//                  X[k1 + 256 (2j+1)] = sum_n O[k1,n] exp(-2 pi i n j/64)   (E/O = A operand, constants = B, resident)
+//                  X[k1 + 256 (2j+1)] = sum_n O[k1,n] exp(-2 pi i n j/64)   (E/O = A operand, written back into the
+//                  TMEM columns of the stage-1 accumulators and read from there; constants = B, resident in smem)
 //   row 128  CUDA  X[128 + 256 k2] from Y[n2,128] = sum_m (-1)^m U[m,n2] + X[128,n2]
-//   power, Hermitian bin map, banded mel dot products, 10 log10(max(1e-10, .)).
+//   power, Hermitian bin map, mel filterbank in moment form (partial moments per <= 43-bin piece by the workers, the
+//   64 filters + 10 log10(max(1e-10, .)) + store by the two helper warps).
+// Warp roles: 16 workers (112 registers after setmaxnreg), MMA issuer, bulk-copy producer, 2 helpers (32 registers).
+// Input: fp32 mono (IN = 0) or interleaved 16-bit PCM with the channel mean fused into the loader (IN = 1, 2, 4, any).
 // GEMM operands are split x = hi + lo (two 16-bit floats) and multiplied as hi*hi + lo*hi + hi*lo with fp32
 // accumulation in TMEM: ~2^-17 relative with bf16 halves, ~2^-22 with fp16 halves (SEDB_SPLIT_FP16=1, which adds a
 // per-frame power-of-two block scale so that the fp16 range is never exceeded).
@@ -80,7 +84,7 @@ constexpr int kWorkerWarps = 16;
 constexpr int kWorkerThreads = kWorkerWarps * 32;
 constexpr int kMmaWarp = 16;
 constexpr int kCopyWarp = 17;
-constexpr int kThreads = 640;                // 16 workers + MMA + copy + 2 idle warps (register allocation is per 4 warps anyway)
+constexpr int kThreads = 640;                // 16 workers + MMA + copy + 2 helper warps (register allocation is per 4 warps anyway)
 constexpr int kWorkerRegs = 112;             // setmaxnreg: the service warp group gives its registers to the workers
 constexpr int kServiceRegs = 32;              // (4 x 32 + 16 x 112) x 32 = the 96 x 640 registers of the launch
 
