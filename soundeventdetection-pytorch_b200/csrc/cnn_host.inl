@@ -404,25 +404,34 @@ int sedb_cnn_forward(sedb_cnn_t* m, const float* x_dev, long long n_clips, long 
 
 }  // extern "C"
 
-// CNN stage of the host pipelines: log-mel image resident in ctx->d_out -> probabilities -> host.
-static int sedb_cnn_forward_pipeline(sedb_ctx_t* c, sedb_cnn_t* cnn, long long n_clips, long long T, float* probs_host) {
-    const size_t need = sedb_cnn_workspace_bytes(cnn, n_clips, T);
-    if (need == 0) return fail("cannot plan the CNN for %lld clips x %lld frames", n_clips, T);
-    if (need > c->d_ws_bytes) {
-        cudaFree(c->d_ws);
-        c->d_ws = nullptr;
-        CUDA_TRY(cudaMalloc(&c->d_ws, need));
-        c->d_ws_bytes = need;
+// CNN stage of the host pipelines: clips [clip0, clip0 + n_group) of the log-mel image resident in ctx->d_out ->
+// probabilities in ctx->d_probs (sized for total_clips).  Called per group of clips while later waveform chunks are
+// still in flight, so that only the last group's forward pass is exposed after the last host->device copy.
+static int sedb_cnn_forward_group(sedb_ctx_t* c, sedb_cnn_t* cnn, long long clip0, long long n_group, long long total_clips,
+                                  long long T, int slot) {
+    const size_t need = sedb_cnn_workspace_bytes(cnn, n_group, T);
+    if (need == 0) return fail("cannot plan the CNN for %lld clips x %lld frames", n_group, T);
+    if (need > c->d_ws_bytes[slot]) {
+        CUDA_TRY(cudaStreamSynchronize(c->s_comp));        // an earlier group may still be using the old workspace
+        cudaFree(c->d_ws[slot]);
+        c->d_ws[slot] = nullptr;
+        CUDA_TRY(cudaMalloc(&c->d_ws[slot], need));
+        c->d_ws_bytes[slot] = need;
     }
-    const size_t n_out = static_cast<size_t>(n_clips) * sedb_cnn_out_frames(cnn, T) * cnn->classes;
+    const size_t per_clip = static_cast<size_t>(sedb_cnn_out_frames(cnn, T)) * cnn->classes;
+    const size_t n_out = static_cast<size_t>(total_clips) * per_clip;
     if (n_out > c->d_probs_elems) {
+        CUDA_TRY(cudaStreamSynchronize(c->s_comp));
         cudaFree(c->d_probs);
         c->d_probs = nullptr;
         CUDA_TRY(cudaMalloc(&c->d_probs, n_out * sizeof(float)));
         c->d_probs_elems = n_out;
     }
-    if (int rc = sedb_cnn_forward(cnn, c->d_out, n_clips, T, nullptr, c->d_probs, c->d_ws, c->d_ws_bytes, c->s_comp))
-        return rc;
+    return sedb_cnn_forward(cnn, c->d_out + clip0 * T * SEDB_MEL_BINS, n_group, T, nullptr, c->d_probs + clip0 * per_clip,
+                            c->d_ws[slot], c->d_ws_bytes[slot], c->s_comp);
+}
+static int sedb_cnn_results_to_host(sedb_ctx_t* c, sedb_cnn_t* cnn, long long n_clips, long long T, float* probs_host) {
+    const size_t n_out = static_cast<size_t>(n_clips) * sedb_cnn_out_frames(cnn, T) * cnn->classes;
     CUDA_TRY(cudaMemcpyAsync(probs_host, c->d_probs, n_out * sizeof(float), cudaMemcpyDeviceToHost, c->s_comp));
     return 0;
 }

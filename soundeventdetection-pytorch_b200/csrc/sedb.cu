@@ -57,8 +57,8 @@ struct sedb_ctx {
     float* d_out = nullptr;
     size_t d_out_elems = 0;
     float* d_norm = nullptr;
-    void* d_ws = nullptr;
-    size_t d_ws_bytes = 0;
+    void* d_ws[2] = {nullptr, nullptr};   // CNN workspaces of the host pipeline: [0] full groups, [1] the odd first group
+    size_t d_ws_bytes[2] = {0, 0};        // (the activation planes keep their zero padding per geometry, see ws_zero_kernel)
     float* d_probs = nullptr;
     size_t d_probs_elems = 0;
 };
@@ -160,7 +160,8 @@ int sedb_destroy(sedb_ctx_t* c) {
     }
     cudaFree(c->d_out);
     cudaFree(c->d_norm);
-    cudaFree(c->d_ws);
+    cudaFree(c->d_ws[0]);
+    cudaFree(c->d_ws[1]);
     cudaFree(c->d_probs);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
     if (c->s_comp) cudaStreamDestroy(c->s_comp);
@@ -303,6 +304,12 @@ static int run_host_pipeline(sedb_ctx_t* c, sedb_cnn_t* cnn, const void* wave_ho
                                  c->s_comp));
         norm_dev = c->d_norm;
     }
+    // The CNN runs per group of kCnnGroup clips behind the log-mel of their chunks, overlapped with the copies still to
+    // come; groups are aligned to the end of the batch (the odd remainder goes first), so that only one full group's
+    // forward pass is exposed after the last host->device copy.
+    const long long kCnnGroup = 64;
+    long long cnn_done = 0;                                            // clips already handed to the CNN
+    long long cnn_next = (n_clips % kCnnGroup) ? (n_clips % kCnnGroup) : (n_clips < kCnnGroup ? n_clips : kCnnGroup);
     int buf = 0;
     for (long long c0 = 0; c0 < n_clips; c0 += chunk, buf ^= 1) {
         const long long nc = (n_clips - c0 < chunk) ? (n_clips - c0) : chunk;
@@ -318,12 +325,21 @@ static int run_host_pipeline(sedb_ctx_t* c, sedb_cnn_t* cnn, const void* wave_ho
                                    c->d_out + c0 * T * SEDB_MEL_BINS, nullptr, c->s_comp, in_fmt, n_channels))
             return rc;
         CUDA_TRY(cudaEventRecord(c->ev_done[buf], c->s_comp));
+        while (cnn && cnn_done + cnn_next <= c0 + nc && cnn_done + cnn_next < n_clips) {
+            if (int rc = sedb_cnn_forward_group(c, cnn, cnn_done, cnn_next, n_clips, T, cnn_next == kCnnGroup ? 0 : 1))
+                return rc;
+            cnn_done += cnn_next;
+            cnn_next = kCnnGroup;
+        }
     }
     if (!cnn) {
         CUDA_TRY(cudaMemcpyAsync(result_host, c->d_out, static_cast<size_t>(n_clips) * T * SEDB_MEL_BINS * sizeof(float),
                                  cudaMemcpyDeviceToHost, c->s_comp));
     } else {
-        if (int rc = sedb_cnn_forward_pipeline(c, cnn, n_clips, T, result_host)) return rc;
+        if (int rc = sedb_cnn_forward_group(c, cnn, cnn_done, n_clips - cnn_done, n_clips, T,
+                                            n_clips - cnn_done == kCnnGroup ? 0 : 1))
+            return rc;
+        if (int rc = sedb_cnn_results_to_host(c, cnn, n_clips, T, result_host)) return rc;
     }
     CUDA_TRY(cudaStreamSynchronize(c->s_comp));
     return 0;
