@@ -141,3 +141,27 @@ def test_end_to_end_host_entry_point():
         ref = torch.sigmoid(cnn_ref.cnn_avgpooling_forward(sd, torch.from_numpy(lm[:, None].astype(np.float32)),
                                                            [2, 2, 2, 1])).numpy()
     assert np.abs(probs.numpy() - ref).max() < TOL_PROB
+
+
+@pytest.mark.parametrize("n_clips", [70, 130])
+def test_host_pipeline_clip_groups_match_the_device_path(n_clips):
+    """sedb_sed_host_f32 runs the CNN per group of 64 clips (odd remainder first) while later chunks are copied; every
+    clip must come out as from the one-shot device path, whatever the group boundaries and chunk sizes."""
+    lib = _ext.load()
+    m, _ = refmodels.seeded_cnn(refmodels.MAIN_CFG)
+    m = m.cuda()
+    n = 126720                                                       # 9 frames -> 8 output frames
+    g = torch.Generator().manual_seed(n_clips)
+    wave = (torch.randn(n_clips, n, generator=g) * torch.logspace(-3, 0, n_clips)[:, None]).pin_memory()
+    handle = m._handle(torch.device("cuda", torch.cuda.current_device()))
+    frames = int(lib.sedb_cnn_out_frames(handle, 9))
+    probs = torch.empty(n_clips, frames, 1).pin_memory()
+    for _ in range(2):                                               # second call reuses both persistent workspaces
+        probs.zero_()
+        _ext.check(lib.sedb_sed_host_f32(_ext.context(), handle, ctypes.c_void_p(wave.data_ptr()), n_clips, n, n, None,
+                                         ctypes.c_void_p(probs.data_ptr())))
+        from sed_b200.dataset.spectogram.preprocess import waveform_to_log_mel
+        with torch.no_grad():
+            ref = m.logits(waveform_to_log_mel(wave.cuda())[:, None]).cpu()
+        assert probs.shape == ref.shape
+        assert (probs - ref).abs().max() < 1e-6
