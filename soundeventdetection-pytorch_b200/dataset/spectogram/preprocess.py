@@ -85,15 +85,14 @@ def pcm16_to_log_mel(pcm, mean=None, std=None) -> torch.Tensor:
     if not _is_int16(pcm):
         raise ValueError("pcm16_to_log_mel expects int16 samples")
     x = pcm if isinstance(pcm, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pcm))
-    x = x.cuda() if not x.is_cuda else x
     if x.dim() == 2:
         x = x[:, :, None]
     if x.dim() != 3:
         raise ValueError("pcm16_to_log_mel expects [B, samples] or [B, samples, channels]")
-    x = x.contiguous()
     B, n, C = x.shape
     if not 1 <= C <= 16:
         raise ValueError("1..16 interleaved channels are supported")
+    x = (x.cuda() if not x.is_cuda else x).contiguous()
     norm = _norm_tensor(mean, std)
     out = torch.empty((B, num_frames(n), cfg.mel_bins), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):

@@ -131,3 +131,16 @@ def test_metric_utils_identical_to_reference_outputs():
     # empty denominators: recall 1 without events, precision 1 without detections
     r, p, ap = M.calculate_metrics(np.zeros((8, 1), np.float32), np.zeros((10, 1)))
     assert np.all(r == 1) and np.all(p == 1) and ap == 0
+
+
+def test_pcm16_argument_validation_needs_no_device():
+    import torch
+    from sed_b200.dataset.spectogram import preprocess as P
+    with pytest.raises(ValueError):
+        P.pcm16_to_log_mel(np.zeros((1, 40000), dtype=np.float32))           # not int16
+    with pytest.raises(ValueError):
+        P.pcm16_to_log_mel(torch.zeros(40000, dtype=torch.int16))            # missing batch dimension
+    with pytest.raises(ValueError):
+        P.pcm16_to_log_mel(torch.zeros(1, 40000, 17, dtype=torch.int16))     # too many channels
+    with pytest.raises(ValueError):
+        P.preprocess_data([], "/tmp/unused", "/tmp/unused.pkl", preprocess_mode="Complex", pcm16=True)
