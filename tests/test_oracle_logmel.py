@@ -107,3 +107,51 @@ def test_split_operand_accuracy(rnd):
     db = 10 * np.log10(np.maximum(1e-10, p @ mel))
     dbr = 10 * np.log10(np.maximum(1e-10, ref @ mel))
     assert np.abs(db - dbr).max() < 1e-3
+
+
+# ---- numerics of the v2 dataflow (fold + radix-2) as the kernel runs it: split operands, per-frame block scale ----
+def _block_scale(g):
+    """2^e with e = 5 - floor(log2 max|g|) rounded down to even (csrc/logmel.cuh)."""
+    mx = np.abs(g).max()
+    if mx == 0:
+        return 1.0
+    e = (5 - int(np.floor(np.log2(mx)))) & ~1
+    return float(2.0 ** max(-56, min(60, e)))
+
+
+def _mel_db(p):
+    return 10 * np.log10(np.maximum(1e-10, p @ R.mel_filter_bank_matrix().astype(np.float64)))
+
+
+def test_v2_dataflow_matches_rfft_exactly_in_float64():
+    g = R.padded_window() * signals.hdr(32768, 5)
+    p, x = dft_model.factored_power_spectrum_v2(g, None)
+    xr = np.fft.rfft(g)
+    assert np.abs(x - xr).max() / np.abs(xr).max() < 1e-6
+
+
+@pytest.mark.parametrize("rnd,window_db", [(dft_model.fp16_round, 100.0), (dft_model.bf16_round, 75.0)])
+def test_dynamic_range_contract_on_a_pure_tone(rnd, window_db):
+    """A pure tone spans > 150 dB per frame in float64.  The split-operand DFT keeps the 1e-2 dB bound for every mel
+    bin within `window_db` of the loudest one and keeps the others below that window."""
+    t = np.arange(32768) / 48000.0
+    g = R.padded_window() * (0.5 * np.sin(2 * np.pi * 1000.0 * t))
+    scale = _block_scale(g) if rnd is dft_model.fp16_round else 1.0
+    p, _ = dft_model.factored_power_spectrum_v2(g, rnd, scale)
+    db, ref = _mel_db(p), _mel_db(np.abs(np.fft.rfft(g)) ** 2)
+    live = ref > ref.max() - window_db
+    assert live.sum() >= 2 and (~live).sum() >= 8            # the tone really exceeds the window
+    assert np.abs(db - ref)[live].max() < 1e-2
+    assert np.all(db[~live] < ref.max() - window_db + 3.0)
+
+
+def test_block_scale_is_what_keeps_quiet_frames_accurate_in_fp16():
+    """1e-4 amplitude: without the power-of-two block scale the fp16 low halves sink into subnormals."""
+    g = R.padded_window() * (1e-4 * signals.white(32768, 9) / 0.1)
+    ref = _mel_db(np.abs(np.fft.rfft(g)) ** 2)
+    scaled, _ = dft_model.factored_power_spectrum_v2(g, dft_model.fp16_round, _block_scale(g))
+    plain, _ = dft_model.factored_power_spectrum_v2(g, dft_model.fp16_round, 1.0)
+    err_scaled, err_plain = np.abs(_mel_db(scaled) - ref).max(), np.abs(_mel_db(plain) - ref).max()
+    assert err_scaled < 1e-3
+    assert err_plain > 5 * err_scaled
+    assert 16.0 <= np.abs(g).max() * _block_scale(g) < 64.0
