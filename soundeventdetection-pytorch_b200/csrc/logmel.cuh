@@ -26,6 +26,8 @@
 #pragma once
 #include "umma.cuh"
 
+// cp.async.bulk.prefetch.L2 of the next frame by the copy warp (0 disables it for A/B measurements: the frame-load
+// phase is 4.2 k cycles with it, 5.8 k without)
 #ifndef SEDB_L2_PREFETCH
 #define SEDB_L2_PREFETCH 1
 #endif
