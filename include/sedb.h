@@ -106,6 +106,11 @@ int sedb_cnn_load(sedb_cnn_t* cnn, const float* const* tensors_dev, int n_tensor
 /* frames produced for T input frames: ratio * floor-pooled(T)  (spectogram_models.py:185-202) */
 long long sedb_cnn_out_frames(const sedb_cnn_t* cnn, long long T);
 size_t sedb_cnn_workspace_bytes(const sedb_cnn_t* cnn, long long n_clips, long long T);
+/* The workspace holds the activation planes; their padding pixels must be zero and the kernels never write them.  The
+ * handle remembers (host-side) for which (workspace pointer, geometry) pairs it has zeroed the padding and zeroes again
+ * only when the pair is new.  It never trusts the memory contents: a caller that frees/re-allocates a workspace, or
+ * lets anything else write into it between calls, must call this first (workspace_dev == NULL forgets all of them). */
+int sedb_cnn_workspace_invalidate(sedb_cnn_t* cnn, const void* workspace_dev);
 /* x_dev: [n_clips, 1, T, 64] float32 log-mel; logits_dev / probs_dev (either may be NULL):
  * [n_clips, out_frames, classes] float32 = forward() / logits() of the reference module. */
 int sedb_cnn_forward(sedb_cnn_t* cnn, const float* x_dev, long long n_clips, long long T, float* logits_dev,
@@ -119,6 +124,7 @@ int sedb_m5_destroy(sedb_m5_t* m5);
  * then fc.weight, fc.bias. */
 int sedb_m5_load(sedb_m5_t* m5, const float* const* tensors_dev, int n_tensors, void* stream);
 size_t sedb_m5_workspace_bytes(const sedb_m5_t* m5, long long n_frames);
+int sedb_m5_workspace_invalidate(sedb_m5_t* m5, const void* workspace_dev);   /* see sedb_cnn_workspace_invalidate */
 /* x_dev: [n_frames, 1, 31680] float32; logits_dev: [n_frames, classes] float32. */
 int sedb_m5_forward(sedb_m5_t* m5, const float* x_dev, long long n_frames, float* logits_dev,
                     void* workspace_dev, size_t workspace_bytes, void* stream);
@@ -151,9 +157,19 @@ int sedb_sed_host_pcm16(sedb_ctx_t* ctx, sedb_cnn_t* cnn, const int16_t* pcm_hos
  * stride; neg_b: set the B-negate bit. */
 int sedb_debug_umma_probe(const float* a_dev, const float* b_dev, float* d_dev, int N, int K, int a_major,
                           int b_major, int pad, int neg_b, int swap_lbo_sbo, void* stream);
+/* Host-only: the decomposition the planner picks for one tensor-core conv layer (cin -> cout, pool, mode 0 = 3x3 2-D /
+ * 1 = k3 1-D, input H x W, amode 0 = inference fp16 / 1 = training bf16 split) over n_img images on num_sms SMs.
+ * out8 = {M tiles per item, N sub-items, fused [wH|wL] MMA, bands per image, rows per band, smem bytes, input plane
+ * pixels, kpb*100 + weight slots*10 + (32-channel pooling pass)}. */
+int sedb_debug_plan_layer(int cin, int cout, int pool, int mode, int ntaps, int H, int W, int amode, long long n_img,
+                          int num_sms, int* out8);
 /* tcgen05.mma issue-to-completion throughput probe: `grid` CTAs each issue `reps` MMAs of 128 x N x 16 over n_acc
  * accumulator tiles; cycles_host receives block 0's total cycles. */
 int sedb_debug_umma_rate(int N, int b_major, int n_acc, int reps, int lbo_a, int lbo_b, int grid,
+                         unsigned long long* cycles_host);
+/* cp.async.bulk global -> shared throughput probe: `grid` CTAs, `nwarps` issuing warps each keeping `depth` copies of
+ * `bytes` in flight, `reps` copies per CTA over nsrc distinct source blocks; cycles_host receives block 0's total cycles. */
+int sedb_debug_bulk_rate(int bytes, int depth, int reps, int nsrc, int spin, int grid, int nwarps,
                          unsigned long long* cycles_host);
 /* Per-phase cycle counters of logmel_fused_kernel (thread 0 of every CTA, summed): enable != 0 switches the
  * instrumentation on; out_host16 (nullable) receives and clears 128 counters (16 for the log-mel kernel, then 16 per

@@ -1,21 +1,29 @@
-// Conv-BN-ReLU(-Pool) blocks of the reference CNNs as implicit-GEMM tcgen05 kernels (inference, BN folded).
+// Conv-BN-ReLU(-Pool) blocks of the reference CNNs as implicit-GEMM tcgen05 kernels.
 //
 //   ConvBlock / Cnn_AvgPooling   models/spectogram_models.py:128-205   (3x3 conv, BN2d, ReLU, AvgPool2d)
 //   M5                           models/waveform_models.py:9-71        (k=3 conv1d, BN1d, ReLU, MaxPool1d(4))
 //
-// Activation layout ("blocked planes"): per image, per split half (hi, lo), per group of 8 channels, a plane of
-// S pixels x 8 channels (16 B per pixel).  Pixels are indexed by the *padded* linear index
-// v = (h+1)*(W+2) + (w+1) (2-D) or v = pos+1 (1-D) behind `lead` zero pixels; padding pixels are zero and are
-// never written.  With this layout
+// Activation layout ("blocked planes"): per image, per group of 8 channels, a plane of S pixels x 8 channels
+// (16 B per pixel).  Pixels are indexed by the *padded* linear index v = (h+1)*(W+2) + (w+1) (2-D) or v = pos+1 (1-D)
+// behind `lead` zero pixels; padding pixels are zero and are never written.  With this layout
 //   * one 1-D bulk copy (TMA engine) stages a K-group of a band of pixels (+halo) into shared memory, already in
 //     the tcgen05 canonical K-major layout (row = pixel, 16 B = 8 channels), and
 //   * the A operand of every filter tap is the same shared-memory patch with the descriptor start address
 //     shifted by (dh*(W+2)+dw) pixels -- no im2col copies.
 // GEMM view: M = pixels (128 per tile, up to 4 tiles per CTA pass), N = C_out tile (<=128), K = taps x C_in.
-// Operands are split bf16 hi/lo (3 MMAs per product, fp32 accumulation in TMEM) so that frame probabilities
-// stay within 1e-3 of the fp32 reference; BN scale/shift and ReLU are applied in fp32 in the epilogue.
+//
+// Two operand regimes (template AMODE):
+//   AMODE 0 (inference, BN folded): activations are ONE fp16 plane set, weights are fp16 hi + lo, two MMAs per
+//            product (a wH + a wL) -- or ONE MMA against the N-concatenated [wH | wL] block when 2 C_out_tile <= 128
+//            columns; fp32 accumulation in TMEM; epilogue = folded-BN scale/shift + ReLU (+ pooling) in fp32, fp16 store.
+//            Measured worst case on frame probabilities: 3e-4 against the 1e-3 gate (weights are exact to 2^-22, only
+//            the activations carry fp16 rounding).
+//   AMODE 1 (training / gradients): activations are bf16 hi + lo plane sets (bf16 keeps the range of fp32, which the
+//            gradients need), weights bf16 hi + lo, three MMAs (aH wH + aL wH + aH wL); epilogue = raw fp32 store
+//            (batch-statistics BatchNorm, ReLU and pooling are separate kernels in train mode).
 #pragma once
 #include "umma.cuh"
+#include "conv_issue.cuh"
 
 namespace sedb {
 
@@ -28,23 +36,27 @@ namespace sedb {
         }                                                                              \
     } while (0)
 
-constexpr int kConvThreads = 320;          // 8 epilogue warps + MMA warp + copy warp
+constexpr int kConvCopyWarps = 4;          // a warp issues one cp.async.bulk per ~500-700 cycles whatever its size
+                                           // (tests/dev/bulk_rate.py), so the copy jobs are dealt round-robin to 4 warps
+constexpr int kConvThreads = 32 * (9 + kConvCopyWarps);   // 8 epilogue warps + MMA warp + copy warps
 constexpr int kConvMaxTiles = 4;            // M tiles (128 pixels) per work item
 constexpr int kConvMaxWSlots = 6;
-constexpr int kConvMaxWSlotBytes = 40960;  // weight ring slot: `kpb` consecutive taps of one 16-channel K-step, hi|lo x [cout_tile][16] each
+constexpr int kConvMaxWSlotBytes = 73728;  // weight ring slot: `kpb` consecutive taps of one 16-channel K-step, [hi | lo] x [cout_tile][16] each
 constexpr int kConvMaxKSteps = 8;          // 16-channel K-steps per input-channel chunk (cin_chunk <= 128)
 constexpr int kConvLead = 8;
 
 struct ConvParams {
     const uint8_t* in;
-    uint8_t* out;
+    uint8_t* out;            // AMODE 0: fp16 blocked planes; AMODE 1: fp32 blocked planes (32 B per pixel per 8-channel group)
     const uint8_t* wpack;
-    const float* scale;      // folded BN scale  [cout]
+    const float* scale;      // folded BN scale  [cout]          (AMODE 0)
     const float* shift;      // folded BN shift (+ conv bias) [cout]
     int n_img, n_bands, n_tiles;
     int mode;                // 0: 2-D 3x3, 1: 1-D k=3
     int H, W, Wp;
     int cin, cout, cin_chunk, n_kchunks, cout_tile, n_ntiles;
+    int n_nsub, cout_sub;    // an N tile is processed as n_nsub work items of cout_sub columns (small batches: more CTAs)
+    int fuse;                // 1: one MMA against [wH | wL] (N = 2 cout_tile); needs n_nsub == 1
     int S_in, S_out;
     int R;                   // rows per band (2-D) ; positions per band = 128*n_tiles (1-D)
     int P, halo;             // patch pixels, halo pixels in front of the band
@@ -52,19 +64,21 @@ struct ConvParams {
     int Ho, Wo, Wpo;
     int ntaps;
     int tapoff[9];           // tap offsets in pixels relative to the patch start
-    int patch_bytes;         // 2 * (cin_chunk/8) * P * 16
+    int patch_bytes;         // narr * (cin_chunk/8) * P * 16   (narr = 1 + AMODE)
     int n_wslots;            // weight ring slots (<= kConvMaxWSlots)
     int kpb;                 // taps per weight ring slot (divides ntaps)
-    int ncat;                // 1: weight block rows are [hi | lo] stacked along N (narrow layers, cout_tile = 32): one
-                             //    N = 2 cout_tile MMA gives aH bH and aH bL, so the A tile is read twice instead of 3 times
     int wslot_bytes;         // kpb * cout_tile * 64
     int stage_bytes;         // pooling stage (0 without pooling)
+    int cstep;               // channels staged per pooling pass (16 or 32)
+    int w_nrep;              // replicas of the packed weights in global memory (CTA b streams replica b % w_nrep): every
+    long long w_rep_bytes;   // CTA reads the same blocks at the same time, replicas spread those reads over more L2 slices
     unsigned long long* prof; // nullable diagnostics: [0] epilogue wait, [1] epilogue work, [2] mma wait patch,
-                              // [3] mma wait weights, [4] mma wait tmem, [5] copy wait patch_free, [6] items
+                              // [3] mma issue, [4] mma wait tmem, [5] copy wait patch_free, [6] items, [7] mma wait weights
 };
 
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 2, 256;" ::: "memory"); }
 
+// 8 channels of one pixel -> bf16 hi + lo halves (training planes)
 __device__ __forceinline__ void store_split8(uint8_t* hi_ptr, uint8_t* lo_ptr, const float* y) {
     uint32_t h[4], l[4];
 #pragma unroll
@@ -80,11 +94,34 @@ __device__ __forceinline__ void store_split8(uint8_t* hi_ptr, uint8_t* lo_ptr, c
     *reinterpret_cast<uint4*>(hi_ptr) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(lo_ptr) = make_uint4(l[0], l[1], l[2], l[3]);
 }
+// 8 channels of one pixel -> fp16 (inference planes); saturates instead of overflowing to inf
+__device__ __forceinline__ void store_h8(uint8_t* ptr, const float* y) {
+    uint32_t h[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __half2 v = __floats2half2_rn(fminf(y[2 * i], 65504.f), fminf(y[2 * i + 1], 65504.f));
+        h[i] = *reinterpret_cast<const uint32_t*>(&v);
+    }
+    *reinterpret_cast<uint4*>(ptr) = make_uint4(h[0], h[1], h[2], h[3]);
+}
+__device__ __forceinline__ void load_h8(const uint8_t* ptr, float* y) {
+    const uint4 v = *reinterpret_cast<const uint4*>(ptr);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+        y[2 * i] = f.x;
+        y[2 * i + 1] = f.y;
+    }
+}
 
 // shared memory: [patch | weight ring | pooling stage | scale/shift | barriers | tmem ptr].  The accumulators are double
 // buffered in TMEM (columns 0..255 / 256..511 for even / odd work items) so that the patch load and the MMAs of item
 // t+1 overlap the epilogue of item t.
+template <int AMODE>
 __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvParams p) {
+    constexpr int kNarr = 1 + AMODE;                       // activation plane sets (AMODE 1: hi, lo)
+    constexpr uint32_t kFmt = AMODE ? kFmtBF16 : kFmtF16;
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* patch = smem;
     uint8_t* wring = smem + ((p.patch_bytes + 127) / 128) * 128;
@@ -122,16 +159,18 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
         mbar_fence_init();
     }
     if (warp == 8) tmem_alloc<512>(tmem_ptr_s);
-    for (int i = tid; i < p.cout; i += kConvThreads) {
-        sc_s[i] = p.scale[i];
-        sh_s[i] = p.shift[i];
-    }
+    if (AMODE == 0)
+        for (int i = tid; i < p.cout; i += kConvThreads) {
+            sc_s[i] = p.scale[i];
+            sh_s[i] = p.shift[i];
+        }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr_s;
 
-    const int items_total = p.n_img * p.n_bands * p.n_ntiles;
+    const int nsplit = p.n_ntiles * p.n_nsub;
+    const int items_total = p.n_img * p.n_bands * nsplit;
     const int n_items = (static_cast<int>(blockIdx.x) < items_total)
                             ? (items_total - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                                   static_cast<int>(gridDim.x)
@@ -142,8 +181,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
     const int blocks_per_kc = p.ntaps * ks_chunk;
     const int group_bytes = p.kpb * wblock_bytes;
 
-    auto decode = [&](int it, int& img, int& band, int& ntile) {
+    auto decode = [&](int it, int& img, int& band, int& ntile, int& nsub) {
         int item = blockIdx.x + it * gridDim.x;
+        nsub = item % p.n_nsub;
+        item /= p.n_nsub;
         ntile = item % p.n_ntiles;
         item /= p.n_ntiles;
         band = item % p.n_bands;
@@ -151,36 +192,44 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
     };
     auto band_v0 = [&](int band) { return p.mode == 0 ? (p.R * band + 1) * p.Wp : 1 + band * 128 * p.n_tiles; };
 
-    if (warp == 9) {
-        // ================================================================ bulk-copy producer (converged warp, one
-        // elected lane issues; see the note in the MMA issuer)
+    if (warp >= 9) {
+        // ================================================================ bulk-copy producers (converged warps, one
+        // elected lane issues; see the note in the MMA issuer).  The copy jobs of an item -- per K-step the patch
+        // groups, then the weight groups -- are dealt round-robin to the copy warps; every job waits on its own slot
+        // barrier, so the warps need no ordering among themselves.
         {
-            int gw = 0;
+            const int cw = warp - 9;
+            int gw = 0, job = 0;
             long long tprev = clock64();
             for (int it = 0; it < n_items; ++it) {
-                int img, band, ntile;
-                decode(it, img, band, ntile);
+                int img, band, ntile, nsub;
+                decode(it, img, band, ntile, nsub);
                 const int v0 = band_v0(band);
                 for (int kc = 0; kc < p.n_kchunks; ++kc) {
                     const int gk = it * p.n_kchunks + kc;
-                    const uint8_t* wsrc = p.wpack + static_cast<long long>(ntile * p.n_kchunks + kc) * blocks_per_kc * wblock_bytes;
+                    const uint8_t* wsrc = p.wpack + static_cast<long long>(blockIdx.x % p.w_nrep) * p.w_rep_bytes +
+                                          static_cast<long long>(ntile * p.n_kchunks + kc) * blocks_per_kc * wblock_bytes;
                     for (int ks = 0; ks < ks_chunk; ++ks) {
-                        tprev = clock64();
-                        if (gk > 0) mbar_wait(&patch_free[ks], (gk - 1) & 1);
-                        CONV_PROF(5);
-                        if (elect_one()) {
-                            mbar_arrive_expect_tx(&patch_full[ks], 4 * p.P * 16);
-                            for (int arr = 0; arr < 2; ++arr)
-                                for (int h = 0; h < 2; ++h) {
-                                    const int kgl = 2 * ks + h;
-                                    const long long plane =
-                                        (static_cast<long long>(img) * 2 + arr) * (p.cin / 8) + kc * kg_chunk + kgl;
-                                    const uint8_t* src = p.in + (plane * p.S_in + kConvLead + v0 - p.halo) * 16;
-                                    bulk_g2s(patch + (arr * kg_chunk + kgl) * p.P * 16, src, p.P * 16, &patch_full[ks]);
-                                }
+                        if ((job++ % kConvCopyWarps) == cw) {
+                            tprev = clock64();
+                            if (gk > 0) mbar_wait(&patch_free[ks], (gk - 1) & 1);
+                            if (cw == 0) { CONV_PROF(5); }
+                            if (elect_one()) {
+                                mbar_arrive_expect_tx(&patch_full[ks], kNarr * 2 * p.P * 16);
+#pragma unroll
+                                for (int arr = 0; arr < kNarr; ++arr)
+                                    for (int h = 0; h < 2; ++h) {
+                                        const int kgl = 2 * ks + h;
+                                        const long long plane =
+                                            (static_cast<long long>(img) * kNarr + arr) * (p.cin / 8) + kc * kg_chunk + kgl;
+                                        const uint8_t* src = p.in + (plane * p.S_in + kConvLead + v0 - p.halo) * 16;
+                                        bulk_g2s(patch + (arr * kg_chunk + kgl) * p.P * 16, src, p.P * 16, &patch_full[ks]);
+                                    }
+                            }
+                            __syncwarp();
                         }
-                        __syncwarp();
                         for (int b = 0; b < p.ntaps; b += p.kpb, ++gw) {
+                            if ((job++ % kConvCopyWarps) != cw) continue;
                             const int s = gw % p.n_wslots, u = gw / p.n_wslots;
                             mbar_wait(&wempty[s], (u & 1) ^ 1);
                             if (elect_one()) {
@@ -199,76 +248,86 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
         // elected lane issues, so that all operands are warp-uniform (TMEM base of the 512-column allocation is 0)
         if (tmem != 0) __trap();
         {
-            const uint32_t idesc = make_idesc(kFmtBF16, kMajorK, kMajorK, 128, p.cout_tile);
-            const uint32_t idesc_cat = make_idesc(kFmtBF16, kMajorK, kMajorK, 128, 2 * p.cout_tile);
-            const uint32_t patch_a = smem_u32(patch);
-            const uint32_t wring_a = smem_u32(wring);
+            const uint32_t idesc = make_idesc(kFmt, kMajorK, kMajorK, 128, p.cout_sub);
+            const uint32_t idesc_cat = make_idesc(kFmt, kMajorK, kMajorK, 128, 2 * p.cout_tile);
             const uint32_t a_lbo = p.P * 16;
-            const uint32_t b_lbo = p.cout_tile * 16 * (p.ncat ? 2 : 1);
-            const uint64_t a_base = make_smem_desc(patch_a, a_lbo, 128);
-            const uint64_t b_base = make_smem_desc(wring_a, b_lbo, 128);
-            const uint32_t a_lo_delta = kg_chunk * p.P;            // lo half of the patch, in 16-byte units
-            const uint32_t b_lo_delta = p.cout_tile * 2;           // lo half of a weight block (separate-halves layout)
+            const uint32_t b_lbo = p.cout_tile * 32;               // [hi | lo] rows of one K-group
+            const uint64_t a_base = make_smem_desc(smem_u32(patch), a_lbo, 128);
+            const uint64_t b_base = make_smem_desc(smem_u32(wring), b_lbo, 128);
+            // descriptors as (lo, hi) words: operands differ in the start-address field of lo only (16-byte units)
+            const uint32_t a_lo0 = static_cast<uint32_t>(a_base), a_hi = static_cast<uint32_t>(a_base >> 32);
+            const uint32_t b_lo0 = static_cast<uint32_t>(b_base), b_hi = static_cast<uint32_t>(b_base >> 32);
+            const uint32_t a_lo_delta = kg_chunk * p.P;            // lo half of the patch, in 16-byte units (AMODE 1)
+            const uint32_t b_lo_delta = p.cout_tile;               // lo rows of a weight block, in 16-byte units
             const uint32_t b_block = p.cout_tile * 4;              // one (tap, K-step) block, in 16-byte units
-            int gw = 0;
+            const uint32_t ct = p.fuse ? 2 * p.cout_tile : p.cout_sub;   // accumulator columns per tile
+            const uint32_t wslot16 = p.wslot_bytes >> 4;
+            const bool fuse = p.fuse != 0;
+            const int n_tiles = p.n_tiles, kpb = p.kpb, ntaps = p.ntaps;
+            int ws = 0;                                         // weight ring slot and its phase
+            uint32_t wph = 0;
             long long tprev = clock64();
             for (int it = 0; it < n_items; ++it) {
+                int img, band, ntile, nsub;
+                decode(it, img, band, ntile, nsub);
                 const uint32_t acc_base = 256 * (it & 1);
+                const uint32_t b_sub = b_lo0 + nsub * p.cout_sub;
                 tprev = clock64();
                 if (it >= 2) {                                  // this accumulator buffer was last drained by item it-2
                     mbar_wait(&epi_done[it & 1], ((it - 2) >> 1) & 1);
                     tc_fence_after();
                 }
                 CONV_PROF(4);
+                uint32_t first = 0u;                            // 0 for the very first MMA of every tile of the item
                 for (int kc = 0; kc < p.n_kchunks; ++kc) {
                     const int gk = it * p.n_kchunks + kc;
-                    // Descriptors differ only in their start-address field (16-byte units, low 14 bits), so every
-                    // operand is the base descriptor plus an offset: the single issuing thread stays a few
-                    // instructions per MMA.
                     for (int ks = 0; ks < ks_chunk; ++ks) {
-                        CONV_PROF(3);                                   // MMA issue (+ weight waits) since the last point
+                        CONV_PROF(3);                                   // MMA issue since the last point
                         mbar_wait(&patch_full[ks], gk & 1);
                         tc_fence_after();
                         CONV_PROF(2);                                   // wait for this K-step's patch groups
-                        const uint32_t ks_off = 2 * ks * p.P;
-                        for (int tap0 = 0; tap0 < p.ntaps; tap0 += p.kpb, ++gw) {
-                            const int s = gw % p.n_wslots, u = gw / p.n_wslots;
-                            mbar_wait(&wfull[s], u & 1);
+                        const uint32_t a_ks = a_lo0 + 2 * ks * p.P;
+                        // one asm statement per weight slot (kpb = 9, 3 or 1 taps): see conv_issue.cuh
+                        for (int tap0 = 0; tap0 < ntaps; tap0 += kpb) {
+                            CONV_PROF(3);
+                            mbar_wait(&wfull[ws], wph);
                             tc_fence_after();
+                            CONV_PROF(7);                               // wait for this slot's weights
                             if (elect_one()) {
-                                uint64_t bH = b_base + static_cast<uint32_t>(s * (p.wslot_bytes >> 4));
-                                for (int j = 0; j < p.kpb; ++j) {
-                                    const uint64_t bL = bH + b_lo_delta;
-                                    const uint32_t acc = (kc > 0 || ks > 0 || tap0 + j > 0) ? 1u : 0u;
-                                    // tiles unrolled with immediate operand offsets: the single issuing lane must
-                                    // not spend more instructions per MMA than a narrow (N = 32) MMA takes to run
-                                    const uint64_t aH = a_base + (ks_off + p.tapoff[tap0 + j]);
-                                    const uint64_t aL = aH + a_lo_delta;
-                                    const uint32_t ct = p.cout_tile * (p.ncat ? 2 : 1);    // accumulator columns per tile
-                                    if (p.ncat) {
-#pragma unroll
-                                        for (int m = 0; m < kConvMaxTiles; ++m) {
-                                            if (m < p.n_tiles) {
-                                                umma_f16(acc_base + m * ct, aH + 128 * m, bH, idesc_cat, acc);   // aH [bH | bL]
-                                                umma_f16(acc_base + m * ct, aL + 128 * m, bH, idesc, 1u);        // aL bH
-                                            }
-                                        }
-                                    } else {
-#pragma unroll
-                                        for (int m = 0; m < kConvMaxTiles; ++m) {
-                                            if (m < p.n_tiles) {
-                                                umma_f16(acc_base + m * ct, aH + 128 * m, bH, idesc, acc);
-                                                umma_f16(acc_base + m * ct, aL + 128 * m, bH, idesc, 1u);
-                                                umma_f16(acc_base + m * ct, aH + 128 * m, bL, idesc, 1u);
-                                            }
-                                        }
-                                    }
-                                    bH += b_block;                   // next tap of the group
+                                const uint32_t b_cur = b_sub + ws * wslot16;
+                                const uint32_t fst = first | static_cast<uint32_t>(tap0);
+#define SEDB_SLOT_ARGS acc_base, ct, a_ks, a_hi, b_cur, b_hi, b_block, b_lo_delta, a_lo_delta, idesc, idesc_cat, fst, n_tiles
+#define SEDB_SLOT_CALL(NT, ...)                                                              \
+    do {                                                                                     \
+        if (AMODE == 0) {                                                                    \
+            if (fuse) conv_slot_a0_fused_##NT(SEDB_SLOT_ARGS, __VA_ARGS__);                  \
+            else conv_slot_a0_split_##NT(SEDB_SLOT_ARGS, __VA_ARGS__);                       \
+        } else {                                                                             \
+            if (fuse) conv_slot_a1_fused_##NT(SEDB_SLOT_ARGS, __VA_ARGS__);                  \
+            else conv_slot_a1_split_##NT(SEDB_SLOT_ARGS, __VA_ARGS__);                       \
+        }                                                                                    \
+    } while (0)
+                                if (kpb == 9) {
+                                    SEDB_SLOT_CALL(9, p.tapoff[0], p.tapoff[1], p.tapoff[2], p.tapoff[3], p.tapoff[4],
+                                                   p.tapoff[5], p.tapoff[6], p.tapoff[7], p.tapoff[8]);
+                                } else if (kpb == 3) {
+                                    if (tap0 == 0) SEDB_SLOT_CALL(3, p.tapoff[0], p.tapoff[1], p.tapoff[2]);
+                                    else if (tap0 == 3) SEDB_SLOT_CALL(3, p.tapoff[3], p.tapoff[4], p.tapoff[5]);
+                                    else SEDB_SLOT_CALL(3, p.tapoff[6], p.tapoff[7], p.tapoff[8]);
+                                } else {
+                                    SEDB_SLOT_CALL(1, p.tapoff[tap0]);
                                 }
-                                umma_commit(&wempty[s]);
+#undef SEDB_SLOT_CALL
+#undef SEDB_SLOT_ARGS
+                                umma_commit(&wempty[ws]);
                             }
                             __syncwarp();
+                            if (++ws == p.n_wslots) {
+                                ws = 0;
+                                wph ^= 1u;
+                            }
                         }
+                        first = 1u;
                         if (elect_one()) umma_commit(&patch_free[ks]);      // this K-step's patch groups may be refilled
                         __syncwarp();
                     }
@@ -287,10 +346,10 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
         const int etid = tid;                                     // 0..255
         long long tprev = clock64();
         for (int it = 0; it < n_items; ++it) {
-            int img, band, ntile;
-            decode(it, img, band, ntile);
+            int img, band, ntile, nsub;
+            decode(it, img, band, ntile, nsub);
             const int v0 = band_v0(band);
-            const int n0 = ntile * p.cout_tile;
+            const int n0 = ntile * p.cout_tile + nsub * p.cout_sub;
             // number of valid band pixels
             int rows_eff = 1, npix;
             if (p.mode == 0) {
@@ -303,9 +362,21 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
             tc_fence_after();
             if (tid == 0) { CONV_PROF(0); }
             const uint32_t tacc = tlane + 256 * (it & 1);
-            const int tile_cols = p.cout_tile * (p.ncat ? 2 : 1);
-            const long long out_img = static_cast<long long>(img) * 2 * (p.cout / 8);
-            if (p.pool == 1) {
+            const int tile_cols = p.fuse ? 2 * p.cout_tile : p.cout_sub;
+            const long long out_img = static_cast<long long>(img) * (p.cout / 8);
+            // 16 accumulator columns of tile m starting at channel c0 (the [wH | wL] halves added when fused)
+            auto load16 = [&](int m, int c0, float* acc) {
+                tmem_ld16(tacc + m * tile_cols + c0, acc);
+                if (p.fuse) {
+                    float acc2[16];
+                    tmem_ld16(tacc + m * tile_cols + p.cout_tile + c0, acc2);
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) acc[i] += acc2[i];
+                }
+                tmem_ld_wait();
+            };
+            if (AMODE == 1 || p.pool == 1) {
                 for (int m = grp; m < p.n_tiles; m += 2) {
                     const int pp = 128 * m + 32 * q + lane;
                     bool valid = pp < npix;
@@ -314,89 +385,88 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                         valid = valid && col >= 1 && col <= p.W;
                     }
                     const long long vout = kConvLead + v0 + pp;
-                    for (int c0 = 0; c0 < p.cout_tile; c0 += 16) {
+                    for (int c0 = 0; c0 < p.cout_sub; c0 += 16) {
                         float acc[16];
-                        tmem_ld16(tacc + m * tile_cols + c0, acc);
-                        if (p.ncat) {                             // add the aH bL half
-                            float acc2[16];
-                            tmem_ld16(tacc + m * tile_cols + p.cout_tile + c0, acc2);
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) acc[i] += acc2[i];
-                        }
-                        tmem_ld_wait();
+                        load16(m, c0, acc);
                         if (valid) {
+                            if (AMODE == 0) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                acc[i] = fmaxf(0.f, fmaf(acc[i], sc_s[n0 + c0 + i], sh_s[n0 + c0 + i]));
+                                for (int i = 0; i < 16; ++i)
+                                    acc[i] = fmaxf(0.f, fmaf(acc[i], sc_s[n0 + c0 + i], sh_s[n0 + c0 + i]));
 #pragma unroll
-                            for (int g2 = 0; g2 < 2; ++g2) {
-                                const long long kg = (n0 + c0) / 8 + g2;
-                                uint8_t* hi = p.out + ((out_img + kg) * p.S_out + vout) * 16;
-                                uint8_t* lo = p.out + ((out_img + (p.cout / 8) + kg) * p.S_out + vout) * 16;
-                                store_split8(hi, lo, acc + 8 * g2);
+                                for (int g2 = 0; g2 < 2; ++g2) {
+                                    const long long kg = (n0 + c0) / 8 + g2;
+                                    store_h8(p.out + ((out_img + kg) * p.S_out + vout) * 16, acc + 8 * g2);
+                                }
+                            } else {
+#pragma unroll
+                                for (int g2 = 0; g2 < 2; ++g2) {
+                                    const long long kg = (n0 + c0) / 8 + g2;
+                                    float4* o = reinterpret_cast<float4*>(p.out + ((out_img + kg) * p.S_out + vout) * 32);
+                                    o[0] = make_float4(acc[8 * g2], acc[8 * g2 + 1], acc[8 * g2 + 2], acc[8 * g2 + 3]);
+                                    o[1] = make_float4(acc[8 * g2 + 4], acc[8 * g2 + 5], acc[8 * g2 + 6], acc[8 * g2 + 7]);
+                                }
                             }
                         }
                     }
                 }
             } else {
-                // pooled: stage 16 channels of every band pixel, then reduce windows
-                for (int c0 = 0; c0 < p.cout_tile; c0 += 16) {
+                // pooled: stage `cstep` channels of every band pixel, then reduce windows
+                const int cstep = p.cstep, sstr = cstep + 1;
+                for (int c0 = 0; c0 < p.cout_sub; c0 += cstep) {
                     for (int m = grp; m < p.n_tiles; m += 2) {
                         const int pp = 128 * m + 32 * q + lane;
-                        float acc[16];
-                        tmem_ld16(tacc + m * tile_cols + c0, acc);
-                        if (p.ncat) {
-                            float acc2[16];
-                            tmem_ld16(tacc + m * tile_cols + p.cout_tile + c0, acc2);
-                            tmem_ld_wait();
+                        for (int c1 = 0; c1 < cstep; c1 += 16) {
+                            float acc[16];
+                            load16(m, c0 + c1, acc);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) acc[i] += acc2[i];
+                            for (int i = 0; i < 16; ++i)
+                                stage[pp * sstr + c1 + i] =
+                                    fmaxf(0.f, fmaf(acc[i], sc_s[n0 + c0 + c1 + i], sh_s[n0 + c0 + c1 + i]));
                         }
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int i = 0; i < 16; ++i)
-                            stage[pp * 17 + i] = fmaxf(0.f, fmaf(acc[i], sc_s[n0 + c0 + i], sh_s[n0 + c0 + i]));
                     }
                     epi_sync();
+                    const int ngrp = cstep / 8;                      // 8-channel groups per pass
                     if (p.mode == 0) {
-                        // avg 2x2: item = (pooled pixel, 8-channel half)
-                        const int half = etid & 1, pix = etid >> 1;
-                        const int r2 = pix / p.Wo, w2 = pix % p.Wo;
-                        const int ho = (p.R / 2) * band + r2;
-                        if (r2 < rows_eff / 2 && ho < p.Ho) {
-                            const int base = (2 * r2) * p.Wp + 2 * w2 + 1;
-                            float y[8];
+                        // avg 2x2: work unit = (pooled pixel, 8-channel group)
+                        const int npool = (p.R / 2) * p.Wo;
+                        for (int u = etid; u < npool * ngrp; u += 256) {
+                            const int half = u % ngrp, pix = u / ngrp;
+                            const int r2 = pix / p.Wo, w2 = pix % p.Wo;
+                            const int ho = (p.R / 2) * band + r2;
+                            if (r2 < rows_eff / 2 && ho < p.Ho) {
+                                const int base = (2 * r2) * p.Wp + 2 * w2 + 1;
+                                float y[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int c = half * 8 + i;
-                                y[i] = 0.25f * (stage[base * 17 + c] + stage[(base + 1) * 17 + c] +
-                                                stage[(base + p.Wp) * 17 + c] + stage[(base + p.Wp + 1) * 17 + c]);
+                                for (int i = 0; i < 8; ++i) {
+                                    const int c = half * 8 + i;
+                                    y[i] = 0.25f * (stage[base * sstr + c] + stage[(base + 1) * sstr + c] +
+                                                    stage[(base + p.Wp) * sstr + c] + stage[(base + p.Wp + 1) * sstr + c]);
+                                }
+                                const long long vout = kConvLead + (ho + 1) * p.Wpo + w2 + 1;
+                                const long long kg = (n0 + c0) / 8 + half;
+                                store_h8(p.out + ((out_img + kg) * p.S_out + vout) * 16, y);
                             }
-                            const long long vout = kConvLead + (ho + 1) * p.Wpo + w2 + 1;
-                            const long long kg = (n0 + c0) / 8 + half;
-                            uint8_t* hi = p.out + ((out_img + kg) * p.S_out + vout) * 16;
-                            uint8_t* lo = p.out + ((out_img + (p.cout / 8) + kg) * p.S_out + vout) * 16;
-                            store_split8(hi, lo, y);
                         }
                     } else {
-                        // max over 4 consecutive positions: item = (pooled position, 8-channel half)
-                        const int half = etid & 1, pos2 = etid >> 1;        // up to 128 pooled positions per band
-                        const int po = band * 32 * p.n_tiles + pos2;
-                        if (pos2 < 32 * p.n_tiles && po < p.Wo) {
-                            float y[8];
+                        // max over 4 consecutive positions: work unit = (pooled position, 8-channel group)
+                        const int npool = 32 * p.n_tiles;
+                        for (int u = etid; u < npool * ngrp; u += 256) {
+                            const int half = u % ngrp, pos2 = u / ngrp;
+                            const int po = band * 32 * p.n_tiles + pos2;
+                            if (po < p.Wo) {
+                                float y[8];
 #pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const int c = half * 8 + i;
-                                const int b0 = 4 * pos2;
-                                y[i] = fmaxf(fmaxf(stage[b0 * 17 + c], stage[(b0 + 1) * 17 + c]),
-                                             fmaxf(stage[(b0 + 2) * 17 + c], stage[(b0 + 3) * 17 + c]));
+                                for (int i = 0; i < 8; ++i) {
+                                    const int c = half * 8 + i;
+                                    const int b0 = 4 * pos2;
+                                    y[i] = fmaxf(fmaxf(stage[b0 * sstr + c], stage[(b0 + 1) * sstr + c]),
+                                                 fmaxf(stage[(b0 + 2) * sstr + c], stage[(b0 + 3) * sstr + c]));
+                                }
+                                const long long vout = kConvLead + 1 + po;
+                                const long long kg = (n0 + c0) / 8 + half;
+                                store_h8(p.out + ((out_img + kg) * p.S_out + vout) * 16, y);
                             }
-                            const long long vout = kConvLead + 1 + po;
-                            const long long kg = (n0 + c0) / 8 + half;
-                            uint8_t* hi = p.out + ((out_img + kg) * p.S_out + vout) * 16;
-                            uint8_t* lo = p.out + ((out_img + (p.cout / 8) + kg) * p.S_out + vout) * 16;
-                            store_split8(hi, lo, y);
                         }
                     }
                     epi_sync();
@@ -417,8 +487,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
 }
 
 // ------------------------------------------------------------------------------------------------------
-// First layer of Cnn_AvgPooling (C_in = audio_channels = 1, K = 9): CUDA cores, fp32, writes blocked planes.
+// First layer of Cnn_AvgPooling (C_in = audio_channels = 1, K = 9): CUDA cores, fp32.
 // x: [n_img, H, W] fp32; w: [cout][9]; one thread per output pixel.
+// (A variant with one thread per (pixel, 8-channel group) -- warp-uniform weight reads, 512-byte warp stores -- was 2.5x
+// slower: the nine input loads and the index arithmetic are then repeated per group.)
+// RAW 0: folded BN + ReLU, fp16 blocked planes (inference); RAW 1: raw convolution, fp32 blocked planes (training).
+template <int RAW>
 __global__ void __launch_bounds__(256) conv_in2d_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                         const float* __restrict__ scale, const float* __restrict__ shift,
                                                         uint8_t* __restrict__ out, int n_img, int H, int W, int cout,
@@ -428,10 +502,11 @@ __global__ void __launch_bounds__(256) conv_in2d_kernel(const float* __restrict_
     float* sc_s = w_s + cout * 9;
     float* sh_s = sc_s + cout;
     for (int i = threadIdx.x; i < cout * 9; i += blockDim.x) w_s[i] = w[i];
-    for (int i = threadIdx.x; i < cout; i += blockDim.x) {
-        sc_s[i] = scale[i];
-        sh_s[i] = shift[i];
-    }
+    if (!RAW)
+        for (int i = threadIdx.x; i < cout; i += blockDim.x) {
+            sc_s[i] = scale[i];
+            sh_s[i] = shift[i];
+        }
     __syncthreads();
     const long long total = static_cast<long long>(n_img) * H * W;
     const int Wp = W + 2;
@@ -450,7 +525,7 @@ __global__ void __launch_bounds__(256) conv_in2d_kernel(const float* __restrict_
                 v[kh * 3 + kw] = (hh >= 0 && hh < H && ww >= 0 && ww < W) ? __ldg(xi + hh * W + ww) : 0.f;
             }
         const long long vout = kConvLead + (h + 1) * Wp + wq + 1;
-        const long long out_img = static_cast<long long>(img) * 2 * (cout / 8);
+        const long long out_img = static_cast<long long>(img) * (cout / 8);
         for (int kg = 0; kg < cout / 8; ++kg) {
             float y[8];
 #pragma unroll
@@ -459,17 +534,23 @@ __global__ void __launch_bounds__(256) conv_in2d_kernel(const float* __restrict_
                 float a = 0.f;
 #pragma unroll
                 for (int t = 0; t < 9; ++t) a = fmaf(v[t], w_s[c * 9 + t], a);
-                y[i] = fmaxf(0.f, fmaf(a, sc_s[c], sh_s[c]));
+                y[i] = RAW ? a : fmaxf(0.f, fmaf(a, sc_s[c], sh_s[c]));
             }
-            uint8_t* hi = out + ((out_img + kg) * S_out + vout) * 16;
-            uint8_t* lo = out + ((out_img + (cout / 8) + kg) * S_out + vout) * 16;
-            store_split8(hi, lo, y);
+            if (RAW) {
+                float4* o = reinterpret_cast<float4*>(out + ((out_img + kg) * S_out + vout) * 32);
+                o[0] = make_float4(y[0], y[1], y[2], y[3]);
+                o[1] = make_float4(y[4], y[5], y[6], y[7]);
+            } else {
+                store_h8(out + ((out_img + kg) * S_out + vout) * 16, y);
+            }
         }
     }
 }
 
 // Head of Cnn_AvgPooling (spectogram_models.py:193-205): mean over freq, Linear, sigmoid, x ratio time repeat.
-// One warp per (image, time step).  in: blocked planes of the last block (C, Hf, Wf).
+// One warp per (image, time step).  in: blocked planes of the last block (C, Hf, Wf): SPLIT 0 = fp16 planes
+// (inference), SPLIT 1 = bf16 hi + lo planes (training).  Lane l handles the 8-channel groups l, l + 32, ...
+template <int SPLIT>
 __global__ void __launch_bounds__(256) head2d_kernel(const uint8_t* __restrict__ in, const float* __restrict__ fc_w,
                                                      const float* __restrict__ fc_b, float* __restrict__ logits,
                                                      float* __restrict__ probs, int n_img, int C, int Hf, int Wf,
@@ -479,20 +560,35 @@ __global__ void __launch_bounds__(256) head2d_kernel(const uint8_t* __restrict__
     if (warp_global >= n_img * Hf) return;
     const int img = warp_global / Hf, h = warp_global % Hf;
     const int Wp = Wf + 2;
-    const long long img_base = static_cast<long long>(img) * 2 * (C / 8);
+    const int nkg = C / 8;
+    const long long img_base = static_cast<long long>(img) * (SPLIT ? 2 : 1) * nkg;
+    const float inv_w = 1.0f / static_cast<float>(Wf);
     for (int cls = 0; cls < classes; ++cls) {
         float acc = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const int kg = c >> 3, ci = c & 7;
-            float s = 0.f;
+        for (int kg = lane; kg < nkg; kg += 32) {
+            float s[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] = 0.f;
             for (int wq = 0; wq < Wf; ++wq) {
                 const long long v = kConvLead + (h + 1) * Wp + wq + 1;
-                const __nv_bfloat16* ph = reinterpret_cast<const __nv_bfloat16*>(in + ((img_base + kg) * S_in + v) * 16);
-                const __nv_bfloat16* pl =
-                    reinterpret_cast<const __nv_bfloat16*>(in + ((img_base + C / 8 + kg) * S_in + v) * 16);
-                s += __bfloat162float(ph[ci]) + __bfloat162float(pl[ci]);
+                float y[8];
+                if (SPLIT) {
+                    const uint4 a = *reinterpret_cast<const uint4*>(in + ((img_base + kg) * S_in + v) * 16);
+                    const uint4 b = *reinterpret_cast<const uint4*>(in + ((img_base + nkg + kg) * S_in + v) * 16);
+                    const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        y[2 * i] = __uint_as_float(wa[i] << 16) + __uint_as_float(wb[i] << 16);
+                        y[2 * i + 1] = __uint_as_float(wa[i] & 0xffff0000u) + __uint_as_float(wb[i] & 0xffff0000u);
+                    }
+                } else {
+                    load_h8(in + ((img_base + kg) * S_in + v) * 16, y);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s[i] += y[i];
             }
-            acc = fmaf(s * (1.0f / static_cast<float>(Wf)), fc_w[cls * C + c], acc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc = fmaf(s[i] * inv_w, fc_w[cls * C + kg * 8 + i], acc);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -657,11 +753,11 @@ __global__ void __launch_bounds__(kFrontThreads, 1) m5_front_kernel(const float*
             const int j = tile * (kFrontTilePos / 4) + (qrow >> 1);               // pooled position
             if ((lane & 1) == 0 && j < L_out) {
                 const long long v = kConvLead + 1 + j;
-                const long long img = static_cast<long long>(frame) * 2 * 8;
+                const long long img = static_cast<long long>(frame) * 8;
 #pragma unroll
                 for (int g2 = 0; g2 < 4; ++g2) {
                     const int kg = 4 * grp + g2;
-                    store_split8(out + ((img + kg) * S_out + v) * 16, out + ((img + 8 + kg) * S_out + v) * 16, y + 8 * g2);
+                    store_h8(out + ((img + kg) * S_out + v) * 16, y + 8 * g2);
                 }
             }
         }
@@ -687,27 +783,30 @@ __global__ void pack_front_weight_kernel(const float* __restrict__ w, uint8_t* _
     *reinterpret_cast<__nv_bfloat16*>(out + 64 * 80 * 2 + off) = l;
 }
 
-// Head of M5 (waveform_models.py:66-67): mean over time, Linear.  One warp per frame.
+// Head of M5 (waveform_models.py:66-67): mean over time, Linear.  One warp per frame; in: fp16 blocked planes.
 __global__ void __launch_bounds__(256) head1d_kernel(const uint8_t* __restrict__ in, const float* __restrict__ fc_w,
                                                      const float* __restrict__ fc_b, float* __restrict__ logits,
                                                      int n, int C, int Lf, int S_in, int classes) {
     const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wg >= n) return;
-    const long long img_base = static_cast<long long>(wg) * 2 * (C / 8);
+    const int nkg = C / 8;
+    const long long img_base = static_cast<long long>(wg) * nkg;
+    const float inv_l = 1.0f / static_cast<float>(Lf);
     for (int cls = 0; cls < classes; ++cls) {
         float acc = 0.f;
-        for (int c = lane; c < C; c += 32) {
-            const int kg = c >> 3, ci = c & 7;
-            float s = 0.f;
+        for (int kg = lane; kg < nkg; kg += 32) {
+            float s[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] = 0.f;
             for (int pos = 0; pos < Lf; ++pos) {
-                const long long v = kConvLead + 1 + pos;
-                const __nv_bfloat16* ph = reinterpret_cast<const __nv_bfloat16*>(in + ((img_base + kg) * S_in + v) * 16);
-                const __nv_bfloat16* pl =
-                    reinterpret_cast<const __nv_bfloat16*>(in + ((img_base + C / 8 + kg) * S_in + v) * 16);
-                s += __bfloat162float(ph[ci]) + __bfloat162float(pl[ci]);
+                float y[8];
+                load_h8(in + ((img_base + kg) * S_in + kConvLead + 1 + pos) * 16, y);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s[i] += y[i];
             }
-            acc = fmaf(s * (1.0f / static_cast<float>(Lf)), fc_w[cls * C + c], acc);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc = fmaf(s[i] * inv_l, fc_w[cls * C + kg * 8 + i], acc);
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -751,45 +850,54 @@ __global__ void bn_fold_kernel(const float* __restrict__ gamma, const float* __r
     shift[i] = beta[i] - mean[i] * s + (bias ? bias[i] * s : 0.f);
 }
 
-// Conv weight [cout][cin][ntaps] fp32 -> blocks [ntile][kc][tap][ks] of {hi,lo} x canonical K-major [cout_tile][16]
+// Conv weight [cout][cin][ntaps] fp32 -> blocks [ntile][kc][ks][tap] of [hi | lo] x canonical K-major [cout_tile][16]:
+// inside each 8-channel K-group the cout_tile hi rows are followed by the cout_tile lo rows, so one block serves as two
+// N = cout_tile operands (or sub-ranges of them) or as ONE N = 2 cout_tile operand.  fp16 != 0: fp16 halves (inference),
+// else bf16 halves (training).  transpose != 0 packs the data-gradient convolution of the same layer instead: output
+// channel = ci, input channel = co, taps reversed (w'[ci][co][t] = w[co][ci][ntaps - 1 - t]); cout/cin/cout_tile/cin_chunk
+// then describe that transposed convolution.
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, uint8_t* __restrict__ out, int cout, int cin,
-                                        int ntaps, int cout_tile, int cin_chunk, int ncat) {
+                                        int ntaps, int cout_tile, int cin_chunk, int fp16, int transpose, int nrep) {
     const long long total = static_cast<long long>(cout) * cin * ntaps;
     const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (idx >= total) return;
     const int tap = static_cast<int>(idx % ntaps);
     const int ci = static_cast<int>((idx / ntaps) % cin);
     const int co = static_cast<int>(idx / (static_cast<long long>(ntaps) * cin));
-    const float v = w[idx];
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    const float v = transpose ? w[(static_cast<long long>(ci) * cout + co) * ntaps + (ntaps - 1 - tap)] : w[idx];
+    uint16_t h16, l16;
+    if (fp16) {
+        const __half h = __float2half_rn(v);
+        const __half l = __float2half_rn(v - __half2float(h));
+        h16 = *reinterpret_cast<const uint16_t*>(&h);
+        l16 = *reinterpret_cast<const uint16_t*>(&l);
+    } else {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+        h16 = *reinterpret_cast<const uint16_t*>(&h);
+        l16 = *reinterpret_cast<const uint16_t*>(&l);
+    }
     const int ntile = co / cout_tile, n = co % cout_tile;
     const int kc = ci / cin_chunk, cil = ci % cin_chunk;
     const int ks = cil / 16, k = cil % 16;
     const int n_kchunks = cin / cin_chunk, ks_chunk = cin_chunk / 16;
     const long long block = ((static_cast<long long>(ntile) * n_kchunks + kc) * ks_chunk + ks) * ntaps + tap;   // K-step major
     const long long base = block * (cout_tile * 64);
-    if (ncat) {      // rows [hi | lo] stacked along N inside each K-group: one N = 2 cout_tile operand
-        const int off = (k / 8) * (cout_tile * 32) + n * 16 + (k % 8) * 2;
-        *reinterpret_cast<__nv_bfloat16*>(out + base + off) = h;
-        *reinterpret_cast<__nv_bfloat16*>(out + base + cout_tile * 16 + off) = l;
-        return;
+    const int off = (k / 8) * (cout_tile * 32) + n * 16 + (k % 8) * 2;
+    const long long rep_bytes = total * 4;                      // hi + lo, 2 bytes each
+    for (int r = 0; r < nrep; ++r) {
+        *reinterpret_cast<uint16_t*>(out + r * rep_bytes + base + off) = h16;
+        *reinterpret_cast<uint16_t*>(out + r * rep_bytes + base + cout_tile * 16 + off) = l16;
     }
-    const int off = (k / 8) * (cout_tile * 16) + n * 16 + (k % 8) * 2;
-    *reinterpret_cast<__nv_bfloat16*>(out + base + off) = h;
-    *reinterpret_cast<__nv_bfloat16*>(out + base + cout_tile * 32 + off) = l;
 }
 
-// Workspace hygiene: padding pixels of every activation plane must be zero.  The first word of the workspace
-// holds a tag describing the geometry it was zeroed for; when it matches nothing is done.
-__global__ void ws_zero_kernel(uint4* __restrict__ ws, long long n16, unsigned long long tag) {
-    const unsigned long long cur = *reinterpret_cast<const volatile unsigned long long*>(ws);
-    if (cur == tag) return;
+// Workspace hygiene: padding pixels of every activation plane must be zero (the kernels never write them).  The host
+// zeroes a workspace whenever its (pointer, geometry) differs from the one it zeroed last; nothing in-band is trusted.
+__global__ void ws_zero_kernel(uint4* __restrict__ ws, long long n16) {
     const uint4 z = make_uint4(0, 0, 0, 0);
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x + 1; i < n16;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n16;
          i += static_cast<long long>(gridDim.x) * blockDim.x)
         ws[i] = z;
 }
-__global__ void ws_tag_kernel(unsigned long long* ws, unsigned long long tag) { ws[0] = tag; ws[1] = 0ull; }
 
 }  // namespace sedb

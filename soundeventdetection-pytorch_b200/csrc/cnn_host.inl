@@ -5,8 +5,9 @@ namespace {
 struct PlaneGeom {          // one blocked activation buffer
     int C = 0, H = 0, W = 0;
     int S = 0;              // pixels per 8-channel plane (incl. lead/tail slack)
+    int elt = 2;            // bytes per element: 2 = fp16 planes, 4 = bf16 hi + lo plane sets or fp32 planes
     size_t offset = 0;      // byte offset inside the workspace
-    size_t bytes_per_img() const { return static_cast<size_t>(2) * (C / 8) * S * 16; }
+    size_t bytes_per_img() const { return static_cast<size_t>(C / 8) * S * 8 * elt; }
 };
 
 struct UmmaLayer {          // a conv layer executed by conv_umma_kernel
@@ -15,16 +16,54 @@ struct UmmaLayer {          // a conv layer executed by conv_umma_kernel
     float* scale = nullptr;
     float* shift = nullptr;
     int cin_chunk = 0, cout_tile = 0;
-    int ncat = 0;             // weight halves stacked along N (see ConvParams::ncat)
+    int nrep = 1;             // replicas of the packed weights (ConvParams::w_nrep)
+    size_t pack_bytes() const { return static_cast<size_t>(cout) * cin * ntaps * 4; }
 };
 
 int round_up(int x, int m) { return (x + m - 1) / m * m; }
-bool conv_fit_smem(sedb::ConvParams& p);
-int plan_umma_layer_tiles(const UmmaLayer& L, int H, int W, int max_tiles, sedb::ConvParams& p);
+int env_int(const char* name, int dflt) {
+    const char* v = std::getenv(name);
+    return v ? std::atoi(v) : dflt;
+}
+const int kFuseMaxCout = env_int("SEDB_FUSE_MAX_COUT", 64);
+const size_t kWeightReplicas = static_cast<size_t>(env_int("SEDB_WEIGHT_REPLICAS", 8));
 
-// Fills the launch parameters of one tensor-core conv layer for an input of H x W (2-D) or length W (1-D) and
-// returns the plane size S the *input* buffer must have.
-int plan_umma_layer(const UmmaLayer& L, int H, int W, sedb::ConvParams& p) {
+size_t conv_smem_bytes(const sedb::ConvParams& p) {
+    const size_t patch = (static_cast<size_t>(p.patch_bytes) + 127) / 128 * 128;
+    return patch + static_cast<size_t>(p.n_wslots) * p.wslot_bytes + p.stage_bytes +
+           static_cast<size_t>(2) * p.cout * 4 + 16 + 32 * 8 + 16 + 128;
+}
+
+// Weight-ring geometry and pooling stage next to the patch: prefer several K-steps per slot (fewer barrier round
+// trips for the MMA issuer), then as many slots as fit.
+bool conv_fit_smem(sedb::ConvParams& p) {
+    const int wblock = p.cout_tile * 64;
+    for (int cstep = (p.pool != 1 && p.cout_sub % 32 == 0) ? 32 : 16; cstep >= 16; cstep -= 16) {
+        p.cstep = cstep;
+        p.stage_bytes = (p.pool != 1) ? 128 * p.n_tiles * (cstep + 1) * 4 : 0;
+        for (int kpb = p.ntaps; kpb >= 1; --kpb) {                 // taps per slot: all of them, 3 or 1 (conv_issue.cuh)
+            if (p.ntaps % kpb || (kpb != p.ntaps && kpb != 3 && kpb != 1) || kpb * wblock > sedb::kConvMaxWSlotBytes)
+                continue;
+            p.kpb = kpb;
+            p.wslot_bytes = kpb * wblock;
+            for (int slots = sedb::kConvMaxWSlots; slots >= (kpb == p.ntaps ? 2 : 3); --slots) {
+                p.n_wslots = slots;
+                if (conv_smem_bytes(p) <= 227 * 1024) return true;
+            }
+        }
+    }
+    p.cstep = 16;
+    p.stage_bytes = (p.pool != 1) ? 128 * p.n_tiles * 17 * 4 : 0;
+    p.kpb = 1;
+    p.wslot_bytes = wblock;
+    p.n_wslots = 2;
+    return conv_smem_bytes(p) <= 227 * 1024;
+}
+
+// Geometry of one candidate decomposition (band of <= max_tiles M tiles, N tile split into n_nsub work items);
+// returns false when it does not fit.  S_in receives the plane size the *input* buffer must have.
+bool plan_candidate(const UmmaLayer& L, int H, int W, int amode, int max_tiles, int n_nsub, int fuse, sedb::ConvParams& p,
+                    int& S_in) {
     p = sedb::ConvParams{};
     p.mode = L.mode;
     p.H = H;
@@ -38,21 +77,25 @@ int plan_umma_layer(const UmmaLayer& L, int H, int W, sedb::ConvParams& p) {
     p.n_ntiles = L.cout / L.cout_tile;
     p.pool = L.pool;
     p.ntaps = L.ntaps;
-    p.ncat = L.ncat;
-    int max_tiles = (L.cin_chunk <= 64) ? sedb::kConvMaxTiles : 2;
-    const int tile_cols = L.cout_tile * (L.ncat ? 2 : 1);
+    p.n_nsub = n_nsub;
+    p.cout_sub = L.cout_tile / n_nsub;
+    if (p.cout_sub % 16 || p.cout_sub < 16) return false;
+    // [wH | wL] as ONE operand (N = 2 cout_tile <= 128): a property of the layer, never of the batch size, so that a
+    // clip's result does not depend on the decomposition chosen for the batch it arrives in (the fused form adds the two
+    // partial sums in the epilogue, the unfused form in the accumulator: different roundings)
+    if (fuse != (L.cout_tile <= kFuseMaxCout ? 1 : 0)) return false;
+    if (fuse && n_nsub != 1) return false;
+    p.fuse = fuse;
+    const int tile_cols = p.fuse ? 2 * p.cout_tile : p.cout_sub;
     if (max_tiles * tile_cols > 256) max_tiles = 256 / tile_cols;       // accumulators are double buffered in TMEM
-    return plan_umma_layer_tiles(L, H, W, max_tiles, p);
-}
-
-int plan_umma_layer_tiles(const UmmaLayer& L, int H, int W, int max_tiles, sedb::ConvParams& p) {
+    if (max_tiles < 1) return false;
     if (L.mode == 0) {
         p.halo = p.Wp + 1;
         int R = (128 * max_tiles) / p.Wp;
         if (L.pool == 2) R &= ~1;
         const int Hcap = (L.pool == 2) ? round_up(H, 2) : H;
         if (R > Hcap) R = Hcap;
-        if (R < L.pool) return -1;
+        if (R < L.pool) return false;
         p.R = R;
         p.n_tiles = (R * p.Wp + 127) / 128;
         p.n_bands = (H + R - 1) / R;
@@ -73,42 +116,58 @@ int plan_umma_layer_tiles(const UmmaLayer& L, int H, int W, int max_tiles, sedb:
         p.Wpo = p.Wo + 2;
     }
     p.P = 128 * p.n_tiles + 2 * p.halo;
-    p.patch_bytes = 2 * (L.cin_chunk / 8) * p.P * 16;
-    if (!conv_fit_smem(p)) {
-        if (max_tiles <= 1) return -1;
-        sedb::ConvParams q = p;                       // keep the layer description, retry with a smaller band
-        q.n_tiles = q.n_bands = q.R = q.P = 0;
-        p = q;
-        return plan_umma_layer_tiles(L, H, W, max_tiles - 1, p);
-    }
+    p.patch_bytes = (1 + amode) * (L.cin_chunk / 8) * p.P * 16;
+    if (!conv_fit_smem(p)) return false;
     const int v0_last = (L.mode == 0) ? (p.R * (p.n_bands - 1) + 1) * p.Wp : 1 + (p.n_bands - 1) * 128 * p.n_tiles;
-    return round_up(sedb::kConvLead + v0_last - p.halo + p.P, 8);
+    S_in = round_up(sedb::kConvLead + v0_last - p.halo + p.P, 8);
+    return true;
 }
 
-size_t conv_smem_bytes(const sedb::ConvParams& p) {
-    const size_t patch = (static_cast<size_t>(p.patch_bytes) + 127) / 128 * 128;
-    return patch + static_cast<size_t>(p.n_wslots) * p.wslot_bytes + p.stage_bytes +
-           static_cast<size_t>(2) * p.cout * 4 + 16 + 32 * 8 + 16 + 128;
+// Measured tcgen05.mma cost (cycles, 128 x N x 16, no-swizzle operands from shared memory; profiles/r1_phase_cycles.md)
+double mma_cycles(int N) { return N <= 32 ? 40.6 : N <= 64 ? 48.6 : N <= 128 ? 64.7 : 129.4; }
+
+// Estimated kernel time (cycles) of a candidate: waves of work items over the SMs, each item bound by its MMAs or by the
+// L2 -> shared-memory stream of its patch and weights, plus a fixed pipeline fill/drain per item.
+double candidate_cost(const sedb::ConvParams& p, int amode, long long n_img, int num_sms) {
+    const double k_steps = static_cast<double>(p.cin / 16) * p.ntaps;
+    double per_tile;
+    if (p.fuse) per_tile = mma_cycles(2 * p.cout_tile) + (amode ? mma_cycles(p.cout_sub) : 0.0);
+    else per_tile = (amode ? 3.0 : 2.0) * mma_cycles(p.cout_sub);
+    const double mma = p.n_tiles * k_steps * per_tile;
+    const double bytes = static_cast<double>(p.patch_bytes) * p.n_kchunks + k_steps * p.cout_tile * 64.0;
+    const long long items = n_img * p.n_bands * p.n_ntiles * p.n_nsub;
+    const long long waves = (items + num_sms - 1) / num_sms;
+    // L2 -> SM: ~6300 B/clk for the whole chip (B300_MICROARCH.md, LTS cap), ~64 B/clk for one SM's bulk copies
+    const double active = static_cast<double>(std::min<long long>(items, num_sms));
+    const double stream = bytes / std::min(64.0, 6300.0 / active);
+    const double epi = p.n_tiles * (p.cout_sub / 16.0) * (p.pool != 1 ? 350.0 : 220.0);
+    const double item = std::max(std::max(mma, stream), epi) + 2500.0;
+    return static_cast<double>(waves) * item + 6000.0;                   // + launch/prologue
 }
 
-// Weight-ring geometry and pooling stage next to the patch: prefer several K-steps per slot (fewer barrier round
-// trips for the MMA issuer), then as many slots as fit.
-bool conv_fit_smem(sedb::ConvParams& p) {
-    p.stage_bytes = (p.pool != 1) ? 128 * p.n_tiles * 17 * 4 : 0;
-    const int wblock = p.cout_tile * 64;
-    for (int kpb = p.ntaps; kpb >= 1; --kpb) {                 // taps per slot: a divisor of the tap count
-        if (p.ntaps % kpb || kpb * wblock > sedb::kConvMaxWSlotBytes) continue;
-        p.kpb = kpb;
-        p.wslot_bytes = kpb * wblock;
-        for (int slots = sedb::kConvMaxWSlots; slots >= 2; --slots) {
-            p.n_wslots = slots;
-            if (conv_smem_bytes(p) <= 227 * 1024) return true;
+// Picks the decomposition of one tensor-core conv layer for an input of H x W (2-D) or length W (1-D) over n_img
+// images and returns the plane size S the *input* buffer must have (-1: unsupported).
+int plan_umma_layer(const UmmaLayer& L, int H, int W, int amode, long long n_img, int num_sms, sedb::ConvParams& best) {
+    double best_cost = 0.0;
+    int best_S = -1;
+    for (int cand = 0; cand < 6; ++cand) {
+        const int n_nsub = 1 << (cand >> 1), fuse = cand & 1;
+        int last_tiles = -1;
+        for (int max_tiles = sedb::kConvMaxTiles; max_tiles >= 1; --max_tiles) {
+            sedb::ConvParams p;
+            int S = 0;
+            if (!plan_candidate(L, H, W, amode, max_tiles, n_nsub, fuse, p, S)) continue;
+            if (p.n_tiles == last_tiles) continue;
+            last_tiles = p.n_tiles;
+            const double c = candidate_cost(p, amode, n_img, num_sms);
+            if (best_S < 0 || c < best_cost * 0.999) {
+                best_cost = c;
+                best_S = S;
+                best = p;
+            }
         }
     }
-    p.kpb = 1;
-    p.wslot_bytes = wblock;
-    p.n_wslots = 2;
-    return conv_smem_bytes(p) <= 227 * 1024;
+    return best_S;
 }
 
 int final_plane_S(int mode, int H, int W) {
@@ -118,10 +177,10 @@ int final_plane_S(int mode, int H, int W) {
 int alloc_layer_params(UmmaLayer& L) {
     L.cin_chunk = L.cin > 128 ? 128 : L.cin;
     L.cout_tile = L.cout > 128 ? 128 : L.cout;
-    L.ncat = (L.cout_tile == 32 && L.mode == 0) ? 1 : 0;
     if (L.cin % 16 || L.cin % L.cin_chunk || L.cout % 16 || L.cout % L.cout_tile)
         return fail("conv layer %d->%d: channel counts must be multiples of 16 (and of 128 above 128)", L.cin, L.cout);
-    CUDA_TRY(cudaMalloc(&L.wpack, static_cast<size_t>(L.cout) * L.cin * L.ntaps * 4));
+    L.nrep = static_cast<int>(std::max<size_t>(1, std::min<size_t>(kWeightReplicas, (8u << 20) / L.pack_bytes())));
+    CUDA_TRY(cudaMalloc(&L.wpack, L.pack_bytes() * L.nrep));
     CUDA_TRY(cudaMalloc(&L.scale, L.cout * sizeof(float)));
     CUDA_TRY(cudaMalloc(&L.shift, L.cout * sizeof(float)));
     return 0;
@@ -134,23 +193,27 @@ void free_layer_params(UmmaLayer& L) {
     L.scale = L.shift = nullptr;
 }
 
-int launch_umma_layer(const sedb_ctx* c, const UmmaLayer& L, sedb::ConvParams p, const uint8_t* in, uint8_t* out,
-                      int n_img, int S_in, int S_out, cudaStream_t st) {
+template <int AMODE>
+int launch_umma_layer(const sedb_ctx* c, const uint8_t* wpack, int w_nrep, size_t w_rep_bytes, const float* scale,
+                      const float* shift, sedb::ConvParams p, const uint8_t* in, uint8_t* out, int n_img, int S_in,
+                      int S_out, cudaStream_t st) {
     p.in = in;
     p.out = out;
-    p.wpack = L.wpack;
-    p.scale = L.scale;
-    p.shift = L.shift;
+    p.wpack = wpack;
+    p.w_nrep = w_nrep;
+    p.w_rep_bytes = static_cast<long long>(w_rep_bytes);
+    p.scale = scale;
+    p.shift = shift;
     p.n_img = n_img;
     p.S_in = S_in;
     p.S_out = S_out;
     p.prof = g_prof ? g_prof + 16 * (1 + (g_conv_layer++ % 7)) : nullptr;
-    const long long items = static_cast<long long>(n_img) * p.n_bands * p.n_ntiles;
+    const long long items = static_cast<long long>(n_img) * p.n_bands * p.n_ntiles * p.n_nsub;
     if (items <= 0) return 0;
     const int grid = static_cast<int>(items < c->num_sms ? items : c->num_sms);
     const size_t smem = conv_smem_bytes(p);
     if (smem > 227 * 1024) return fail("conv layer needs %zu bytes of shared memory", smem);
-    sedb::conv_umma_kernel<<<grid, sedb::kConvThreads, smem, st>>>(p);
+    sedb::conv_umma_kernel<AMODE><<<grid, sedb::kConvThreads, smem, st>>>(p);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -160,7 +223,7 @@ int fold_and_pack(UmmaLayer& L, const float* w, const float* bias, const float* 
                   const float* mean, const float* var, cudaStream_t st) {
     const long long total = static_cast<long long>(L.cout) * L.cin * L.ntaps;
     sedb::pack_conv_weight_kernel<<<static_cast<int>((total + 255) / 256), 256, 0, st>>>(w, L.wpack, L.cout, L.cin,
-                                                                                      L.ntaps, L.cout_tile, L.cin_chunk, L.ncat);
+                                                                                      L.ntaps, L.cout_tile, L.cin_chunk, 1, 0, L.nrep);
     sedb::bn_fold_kernel<<<(L.cout + 127) / 128, 128, 0, st>>>(gamma, beta, mean, var, bias, 1e-5f, L.cout, L.scale,
                                                               L.shift);
     g_launches.fetch_add(2);
@@ -168,11 +231,35 @@ int fold_and_pack(UmmaLayer& L, const float* w, const float* bias, const float* 
     return 0;
 }
 
-int prepare_workspace(void* ws, size_t bytes, unsigned long long tag, cudaStream_t st) {
-    sedb::ws_zero_kernel<<<1184, 256, 0, st>>>(reinterpret_cast<uint4*>(ws), static_cast<long long>(bytes / 16), tag);
-    sedb::ws_tag_kernel<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long*>(ws), tag);
-    g_launches.fetch_add(2);
+// Host-side record of which workspaces hold zeroed padding for which geometry.  Nothing in-band is trusted: a caller
+// that lets anything else write a workspace between calls (or frees and re-allocates it) must invalidate it.
+struct ZeroedSet {
+    struct Entry { const void* ptr; unsigned long long tag; };
+    std::vector<Entry> entries;
+    bool has(const void* ptr, unsigned long long tag) const {
+        for (const auto& e : entries)
+            if (e.ptr == ptr && e.tag == tag) return true;
+        return false;
+    }
+    void put(const void* ptr, unsigned long long tag) {
+        for (auto& e : entries)
+            if (e.ptr == ptr) { e.tag = tag; return; }
+        if (entries.size() >= 8) entries.erase(entries.begin());
+        entries.push_back({ptr, tag});
+    }
+    void drop(const void* ptr) {
+        if (!ptr) { entries.clear(); return; }
+        for (size_t i = 0; i < entries.size(); ++i)
+            if (entries[i].ptr == ptr) { entries.erase(entries.begin() + i); return; }
+    }
+};
+
+int prepare_workspace(ZeroedSet& z, void* ws, size_t bytes, unsigned long long tag, cudaStream_t st) {
+    if (z.has(ws, tag)) return 0;
+    sedb::ws_zero_kernel<<<592, 256, 0, st>>>(reinterpret_cast<uint4*>(ws), static_cast<long long>(bytes / 16));
+    g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
+    z.put(ws, tag);
     return 0;
 }
 
@@ -184,6 +271,14 @@ unsigned long long mix_tag(unsigned long long h, unsigned long long v) {
 }  // namespace
 
 // ============================================================================================ Cnn_AvgPooling
+struct CnnPlan {
+    std::vector<PlaneGeom> planes;            // planes[0] = output of block0.conv1, planes[i+1] = output of layers[i]
+    std::vector<sedb::ConvParams> params;     // per umma layer
+    size_t ws_bytes = 0;
+    int Hf = 0, Wf = 0;
+    unsigned long long tag = 0;
+};
+
 struct sedb_cnn {
     sedb_ctx* ctx = nullptr;
     int n_blocks = 0, classes = 0;
@@ -197,14 +292,9 @@ struct sedb_cnn {
     float* fc_w = nullptr;            // [classes][C_last]
     float* fc_b = nullptr;
     bool loaded = false;
-};
-
-struct CnnPlan {
-    std::vector<PlaneGeom> planes;            // planes[0] = output of block0.conv1, planes[i+1] = output of layers[i]
-    std::vector<sedb::ConvParams> params;     // per umma layer
-    size_t ws_bytes = 0;
-    int Hf = 0, Wf = 0;
-    unsigned long long tag = 0;
+    std::map<std::pair<long long, long long>, CnnPlan> plans;   // (n_clips, T) -> plan, built once per shape
+    ZeroedSet zeroed;
+    struct sedb_cnn_train* train = nullptr;                       // training-step state (cnn_train_host.inl), lazily built
 };
 
 static int cnn_make_plan(const sedb_cnn* m, long long n_clips, long long T, CnnPlan& plan) {
@@ -217,8 +307,8 @@ static int cnn_make_plan(const sedb_cnn* m, long long n_clips, long long T, CnnP
     plan.planes[0].W = W;
     for (int i = 0; i < nl; ++i) {
         const UmmaLayer& L = m->layers[i];
-        const int S_in = plan_umma_layer(L, H, W, plan.params[i]);
-        if (S_in < 0) return fail("unsupported feature-map width %d", W);
+        const int S_in = plan_umma_layer(L, H, W, 0, n_clips, m->ctx->num_sms, plan.params[i]);
+        if (S_in < 0) return fail("unsupported feature-map size %d x %d", H, W);
         plan.planes[i].S = S_in;
         H = plan.params[i].Ho;
         W = plan.params[i].Wo;
@@ -231,7 +321,7 @@ static int cnn_make_plan(const sedb_cnn* m, long long n_clips, long long T, CnnP
     plan.planes[nl].S = final_plane_S(0, H, W);
     plan.Hf = H;
     plan.Wf = W;
-    size_t off = 128;                                   // header: geometry tag
+    size_t off = 0;
     unsigned long long tag = mix_tag(0x5EDBull, static_cast<unsigned long long>(n_clips));
     tag = mix_tag(tag, static_cast<unsigned long long>(T));
     for (auto& g : plan.planes) {
@@ -244,13 +334,32 @@ static int cnn_make_plan(const sedb_cnn* m, long long n_clips, long long T, CnnP
     return 0;
 }
 
+// plan for (n_clips, T), built on first use and kept in the handle (a forward call then costs the launches only)
+static int cnn_get_plan(sedb_cnn* m, long long n_clips, long long T, const CnnPlan** out) {
+    const auto key = std::make_pair(n_clips, T);
+    auto it = m->plans.find(key);
+    if (it == m->plans.end()) {
+        CnnPlan plan;
+        if (int rc = cnn_make_plan(m, n_clips, T, plan)) return rc;
+        if (m->plans.size() >= 64) m->plans.clear();
+        it = m->plans.emplace(key, std::move(plan)).first;
+    }
+    *out = &it->second;
+    return 0;
+}
+
 static int sedb_cnn_kernels_init() {
-    CUDA_TRY(cudaFuncSetAttribute(sedb::conv_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(sedb::conv_umma_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(sedb::conv_umma_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(sedb::m5_front_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, sedb::kFrontSmem));
     return 0;
 }
 
+static void sedb_cnn_train_free(sedb_cnn* m);
+
 extern "C" {
+
+int sedb_cnn_destroy(sedb_cnn_t* m);
 
 int sedb_cnn_create(sedb_ctx_t* ctx, const int* channels, const int* pools, int n_blocks, int classes_num,
                     sedb_cnn_t** out) {
@@ -266,6 +375,11 @@ int sedb_cnn_create(sedb_ctx_t* ctx, const int* channels, const int* pools, int 
     }
     sedb_cnn* m = new (std::nothrow) sedb_cnn();
     if (!m) return fail("out of host memory");
+    // every failure below releases what has been allocated so far (the caller never sees a partial object)
+    struct Guard {
+        sedb_cnn* m;
+        ~Guard() { if (m) sedb_cnn_destroy(m); }
+    } guard{m};
     m->ctx = ctx;
     m->n_blocks = n_blocks;
     m->classes = classes_num;
@@ -282,28 +396,30 @@ int sedb_cnn_create(sedb_ctx_t* ctx, const int* channels, const int* pools, int 
     CUDA_TRY(cudaMalloc(&m->shift_in, C0 * sizeof(float)));
     for (int b = 0; b < n_blocks; ++b) {
         if (b > 0) {
-            UmmaLayer L;
+            m->layers.emplace_back();
+            UmmaLayer& L = m->layers.back();
             L.cin = channels[b - 1];
             L.cout = channels[b];
             L.pool = 1;
             if (int rc = alloc_layer_params(L)) return rc;
-            m->layers.push_back(L);
         }
-        UmmaLayer L;
+        m->layers.emplace_back();
+        UmmaLayer& L = m->layers.back();
         L.cin = channels[b];
         L.cout = channels[b];
         L.pool = pools[b];
         if (int rc = alloc_layer_params(L)) return rc;
-        m->layers.push_back(L);
     }
     CUDA_TRY(cudaMalloc(&m->fc_w, static_cast<size_t>(classes_num) * channels[n_blocks - 1] * sizeof(float)));
     CUDA_TRY(cudaMalloc(&m->fc_b, classes_num * sizeof(float)));
+    guard.m = nullptr;
     *out = m;
     return 0;
 }
 
 int sedb_cnn_destroy(sedb_cnn_t* m) {
     if (!m) return 0;
+    sedb_cnn_train_free(m);
     cudaFree(m->w_in);
     cudaFree(m->scale_in);
     cudaFree(m->shift_in);
@@ -353,9 +469,15 @@ long long sedb_cnn_out_frames(const sedb_cnn_t* m, long long T) {
 
 size_t sedb_cnn_workspace_bytes(const sedb_cnn_t* m, long long n_clips, long long T) {
     if (!m || n_clips <= 0 || T <= 0) return 0;
-    CnnPlan plan;
-    if (cnn_make_plan(m, n_clips, T, plan)) return 0;
-    return plan.ws_bytes;
+    const CnnPlan* plan = nullptr;
+    if (cnn_get_plan(const_cast<sedb_cnn_t*>(m), n_clips, T, &plan)) return 0;
+    return plan->ws_bytes;
+}
+
+int sedb_cnn_workspace_invalidate(sedb_cnn_t* m, const void* workspace_dev) {
+    if (!m) return fail("sedb_cnn_workspace_invalidate: null handle");
+    m->zeroed.drop(workspace_dev);
+    return 0;
 }
 
 int sedb_cnn_forward(sedb_cnn_t* m, const float* x_dev, long long n_clips, long long T, float* logits_dev,
@@ -367,12 +489,13 @@ int sedb_cnn_forward(sedb_cnn_t* m, const float* x_dev, long long n_clips, long 
     if (n_clips == 0) return 0;
     if (reinterpret_cast<uintptr_t>(workspace_dev) & 127) return fail("workspace must be 128-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    CnnPlan plan;
-    if (int rc = cnn_make_plan(m, n_clips, T, plan)) return rc;
+    const CnnPlan* planp = nullptr;
+    if (int rc = cnn_get_plan(m, n_clips, T, &planp)) return rc;
+    const CnnPlan& plan = *planp;
     if (workspace_bytes < plan.ws_bytes)
         return fail("sedb_cnn_forward: workspace has %zu bytes, needs %zu", workspace_bytes, plan.ws_bytes);
     uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
-    if (int rc = prepare_workspace(ws, plan.ws_bytes, plan.tag, st)) return rc;
+    if (int rc = prepare_workspace(m->zeroed, ws, plan.ws_bytes, plan.tag, st)) return rc;
     const int n_img = static_cast<int>(n_clips);
     {   // block 0 conv1
         const PlaneGeom& g = plan.planes[0];
@@ -380,22 +503,23 @@ int sedb_cnn_forward(sedb_cnn_t* m, const float* x_dev, long long n_clips, long 
         long long blocks = (total + 255) / 256;
         if (blocks > 148LL * 16) blocks = 148LL * 16;
         const size_t smem = static_cast<size_t>(g.C) * 11 * sizeof(float);
-        sedb::conv_in2d_kernel<<<static_cast<int>(blocks), 256, smem, st>>>(x_dev, m->w_in, m->scale_in, m->shift_in,
-                                                                           ws + g.offset, n_img, g.H, g.W, g.C, g.S);
+        sedb::conv_in2d_kernel<0><<<static_cast<int>(blocks), 256, smem, st>>>(x_dev, m->w_in, m->scale_in, m->shift_in,
+                                                                              ws + g.offset, n_img, g.H, g.W, g.C, g.S);
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
     }
     for (size_t i = 0; i < m->layers.size(); ++i) {
-        if (int rc = launch_umma_layer(m->ctx, m->layers[i], plan.params[i], ws + plan.planes[i].offset,
-                                       ws + plan.planes[i + 1].offset, n_img, plan.planes[i].S, plan.planes[i + 1].S, st))
+        const UmmaLayer& L = m->layers[i];
+        if (int rc = launch_umma_layer<0>(m->ctx, L.wpack, L.nrep, L.pack_bytes(), L.scale, L.shift, plan.params[i], ws + plan.planes[i].offset,
+                                          ws + plan.planes[i + 1].offset, n_img, plan.planes[i].S, plan.planes[i + 1].S, st))
             return rc;
     }
     {
         const PlaneGeom& g = plan.planes.back();
         const long long warps = static_cast<long long>(n_img) * plan.Hf;
         const int blocks = static_cast<int>((warps * 32 + 255) / 256);
-        sedb::head2d_kernel<<<blocks, 256, 0, st>>>(ws + g.offset, m->fc_w, m->fc_b, logits_dev, probs_dev, n_img, g.C,
-                                                   plan.Hf, plan.Wf, g.S, m->classes, m->ratio);
+        sedb::head2d_kernel<0><<<blocks, 256, 0, st>>>(ws + g.offset, m->fc_w, m->fc_b, logits_dev, probs_dev, n_img, g.C,
+                                                      plan.Hf, plan.Wf, g.S, m->classes, m->ratio);
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
     }
@@ -413,6 +537,7 @@ static int sedb_cnn_forward_group(sedb_ctx_t* c, sedb_cnn_t* cnn, long long clip
     if (need == 0) return fail("cannot plan the CNN for %lld clips x %lld frames", n_group, T);
     if (need > c->d_ws_bytes[slot]) {
         CUDA_TRY(cudaStreamSynchronize(c->s_comp));        // an earlier group may still be using the old workspace
+        cnn->zeroed.drop(c->d_ws[slot]);
         cudaFree(c->d_ws[slot]);
         c->d_ws[slot] = nullptr;
         CUDA_TRY(cudaMalloc(&c->d_ws[slot], need));
@@ -437,6 +562,14 @@ static int sedb_cnn_results_to_host(sedb_ctx_t* c, sedb_cnn_t* cnn, long long n_
 }
 
 // ============================================================================================ M5
+struct M5Plan {
+    std::vector<PlaneGeom> planes;
+    std::vector<sedb::ConvParams> params;
+    size_t ws_bytes = 0;
+    int Lf = 0;
+    unsigned long long tag = 0;
+};
+
 struct sedb_m5 {
     sedb_ctx* ctx = nullptr;
     int classes = 0;
@@ -448,14 +581,8 @@ struct sedb_m5 {
     float* fc_w = nullptr;            // [classes][256]
     float* fc_b = nullptr;
     bool loaded = false;
-};
-
-struct M5Plan {
-    std::vector<PlaneGeom> planes;
-    std::vector<sedb::ConvParams> params;
-    size_t ws_bytes = 0;
-    int Lf = 0;
-    unsigned long long tag = 0;
+    std::map<long long, M5Plan> plans;
+    ZeroedSet zeroed;
 };
 
 static const int kM5Cin[8] = {64, 64, 64, 64, 64, 128, 128, 256};
@@ -471,7 +598,7 @@ static int m5_make_plan(const sedb_m5* m, long long n_frames, M5Plan& plan) {
     plan.planes[0].H = 1;
     plan.planes[0].W = L;
     for (int i = 0; i < 8; ++i) {
-        const int S_in = plan_umma_layer(m->layers[i], 1, L, plan.params[i]);
+        const int S_in = plan_umma_layer(m->layers[i], 1, L, 0, n_frames, m->ctx->num_sms, plan.params[i]);
         if (S_in < 0) return fail("m5 planning failed");
         plan.planes[i].S = S_in;
         if (m->layers[i].pool != 1) L = plan.params[i].Wo;
@@ -481,7 +608,7 @@ static int m5_make_plan(const sedb_m5* m, long long n_frames, M5Plan& plan) {
     }
     plan.planes[8].S = final_plane_S(1, 1, L);
     plan.Lf = L;
-    size_t off = 128;
+    size_t off = 0;
     unsigned long long tag = mix_tag(0x35ull, static_cast<unsigned long long>(n_frames));
     for (auto& g : plan.planes) {
         g.offset = off;
@@ -493,7 +620,21 @@ static int m5_make_plan(const sedb_m5* m, long long n_frames, M5Plan& plan) {
     return 0;
 }
 
+static int m5_get_plan(sedb_m5* m, long long n_frames, const M5Plan** out) {
+    auto it = m->plans.find(n_frames);
+    if (it == m->plans.end()) {
+        M5Plan plan;
+        if (int rc = m5_make_plan(m, n_frames, plan)) return rc;
+        if (m->plans.size() >= 64) m->plans.clear();
+        it = m->plans.emplace(n_frames, std::move(plan)).first;
+    }
+    *out = &it->second;
+    return 0;
+}
+
 extern "C" {
+
+int sedb_m5_destroy(sedb_m5_t* m);
 
 int sedb_m5_create(sedb_ctx_t* ctx, int classes_num, sedb_m5_t** out) {
     if (!ctx || !out) return fail("sedb_m5_create: null argument");
@@ -501,6 +642,10 @@ int sedb_m5_create(sedb_ctx_t* ctx, int classes_num, sedb_m5_t** out) {
     if (classes_num < 1) return fail("sedb_m5_create: classes_num must be positive");
     sedb_m5* m = new (std::nothrow) sedb_m5();
     if (!m) return fail("out of host memory");
+    struct Guard {
+        sedb_m5* m;
+        ~Guard() { if (m) sedb_m5_destroy(m); }
+    } guard{m};
     m->ctx = ctx;
     m->classes = classes_num;
     CUDA_TRY(cudaMalloc(&m->w_in, 64 * 80 * sizeof(float)));
@@ -508,17 +653,18 @@ int sedb_m5_create(sedb_ctx_t* ctx, int classes_num, sedb_m5_t** out) {
     CUDA_TRY(cudaMalloc(&m->scale_in, 64 * sizeof(float)));
     CUDA_TRY(cudaMalloc(&m->shift_in, 64 * sizeof(float)));
     for (int i = 0; i < 8; ++i) {
-        UmmaLayer L;
+        m->layers.emplace_back();
+        UmmaLayer& L = m->layers.back();
         L.cin = kM5Cin[i];
         L.cout = kM5Cout[i];
         L.pool = kM5Pool[i];
         L.mode = 1;
         L.ntaps = 3;
         if (int rc = alloc_layer_params(L)) return rc;
-        m->layers.push_back(L);
     }
     CUDA_TRY(cudaMalloc(&m->fc_w, static_cast<size_t>(classes_num) * 256 * sizeof(float)));
     CUDA_TRY(cudaMalloc(&m->fc_b, classes_num * sizeof(float)));
+    guard.m = nullptr;
     *out = m;
     return 0;
 }
@@ -560,9 +706,15 @@ int sedb_m5_load(sedb_m5_t* m, const float* const* t, int n_tensors, void* strea
 
 size_t sedb_m5_workspace_bytes(const sedb_m5_t* m, long long n_frames) {
     if (!m || n_frames <= 0) return 0;
-    M5Plan plan;
-    if (m5_make_plan(m, n_frames, plan)) return 0;
-    return plan.ws_bytes;
+    const M5Plan* plan = nullptr;
+    if (m5_get_plan(const_cast<sedb_m5_t*>(m), n_frames, &plan)) return 0;
+    return plan->ws_bytes;
+}
+
+int sedb_m5_workspace_invalidate(sedb_m5_t* m, const void* workspace_dev) {
+    if (!m) return fail("sedb_m5_workspace_invalidate: null handle");
+    m->zeroed.drop(workspace_dev);
+    return 0;
 }
 
 int sedb_m5_forward(sedb_m5_t* m, const float* x_dev, long long n_frames, float* logits_dev, void* workspace_dev,
@@ -573,12 +725,13 @@ int sedb_m5_forward(sedb_m5_t* m, const float* x_dev, long long n_frames, float*
     if (n_frames == 0) return 0;
     if (reinterpret_cast<uintptr_t>(workspace_dev) & 127) return fail("workspace must be 128-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    M5Plan plan;
-    if (int rc = m5_make_plan(m, n_frames, plan)) return rc;
+    const M5Plan* planp = nullptr;
+    if (int rc = m5_get_plan(m, n_frames, &planp)) return rc;
+    const M5Plan& plan = *planp;
     if (workspace_bytes < plan.ws_bytes)
         return fail("sedb_m5_forward: workspace has %zu bytes, needs %zu", workspace_bytes, plan.ws_bytes);
     uint8_t* ws = static_cast<uint8_t*>(workspace_dev);
-    if (int rc = prepare_workspace(ws, plan.ws_bytes, plan.tag, st)) return rc;
+    if (int rc = prepare_workspace(m->zeroed, ws, plan.ws_bytes, plan.tag, st)) return rc;
     const int n = static_cast<int>(n_frames);
     {
         const PlaneGeom& g = plan.planes[0];
@@ -591,8 +744,9 @@ int sedb_m5_forward(sedb_m5_t* m, const float* x_dev, long long n_frames, float*
         CUDA_TRY(cudaGetLastError());
     }
     for (int i = 0; i < 8; ++i) {
-        if (int rc = launch_umma_layer(m->ctx, m->layers[i], plan.params[i], ws + plan.planes[i].offset,
-                                       ws + plan.planes[i + 1].offset, n, plan.planes[i].S, plan.planes[i + 1].S, st))
+        const UmmaLayer& L = m->layers[i];
+        if (int rc = launch_umma_layer<0>(m->ctx, L.wpack, L.nrep, L.pack_bytes(), L.scale, L.shift, plan.params[i], ws + plan.planes[i].offset,
+                                          ws + plan.planes[i + 1].offset, n, plan.planes[i].S, plan.planes[i + 1].S, st))
             return rc;
     }
     {

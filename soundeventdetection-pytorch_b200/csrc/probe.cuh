@@ -105,12 +105,13 @@ __global__ void __launch_bounds__(128, 1) umma_probe_kernel(const float* __restr
 __global__ void __launch_bounds__(128, 1) umma_rate_kernel(unsigned long long* out, int N, int b_major, int n_acc,
                                                            int reps, int lbo_a, int lbo_b) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bar;
+    __shared__ uint64_t bar, bar2;
     __shared__ uint32_t tmem_ptr;
     const int tid = threadIdx.x, warp = tid >> 5;
     for (int i = tid; i < 64 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
     if (tid == 0) {
         mbar_init(&bar, 1);
+        mbar_init(&bar2, 1);
         mbar_fence_init();
     }
     if (warp == 0) tmem_alloc<512>(&tmem_ptr);
@@ -122,7 +123,8 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(unsigned long long* o
     const int mode = lbo_b >> 24;          // 0: lane-0 branch, 1: converged warp + elect
     lbo_b &= 0xffffff;
     const uint32_t a_off = static_cast<uint32_t>(lbo_a >> 24) * 16;   // A start offset (bytes, 16-byte units): tap shifts
-    lbo_a &= 0xffffff;
+    const int commit_log2 = (lbo_a >> 20) & 0xf;
+    lbo_a &= 0xfffff;
     if (mode == 0) {
         if (tid == 0) {
             const uint32_t idesc = make_idesc(kFmtF16, kMajorK, b_major, 128, N);
@@ -135,7 +137,35 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(unsigned long long* o
             const long long t1 = clock64();
             if (blockIdx.x == 0) out[0] = static_cast<unsigned long long>(t1 - t0);
         }
-    } else if (warp == 1) {
+    } else if (mode == 2 && warp == 1) {
+        // operand-switch probe: MMA r accumulates into tile r % n_acc, reads B block (r / b_run) % nb (blocks 4 KB apart)
+        // and A view r % 8 (shifted by 16 bytes); lbo_b carries nb in bits 12..15 and b_run in bits 16..23
+        if (tmem != 0) __trap();
+        const int nb = (lbo_b >> 12) & 0xf, b_run = (lbo_b >> 16) & 0xff;
+        const uint32_t idesc = make_idesc(kFmtF16, kMajorK, b_major, 128, N);
+        const uint64_t da = make_smem_desc(smem_u32(smem) + a_off, lbo_a, 128);
+        const uint64_t db = make_smem_desc(smem_u32(smem) + 16384, 2048, 128);
+        const long long t0 = clock64();
+        // n_acc, nb, b_run are powers of two (masks and shifts only on the issuing thread)
+        // bits 20..23 of lbo_a: log2 of the commit interval (0 = only at the end); commits go to a barrier nobody waits on
+        const uint32_t am = n_acc - 1, bm = nb - 1;
+        const int bs = 31 - __clz(b_run);
+        const int cint = commit_log2 ? (1 << commit_log2) : (1 << 30);
+        for (int r = 0; r < reps; r += 4) {
+            if (elect_one()) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    umma_f16(((r + q) & am) * 128, da + ((r + q) & 7), db + (((r + q) >> bs) & bm) * 256, idesc, 1u);
+                if (((r + 4) & (cint - 1)) == 0) umma_commit(&bar2);
+            }
+            __syncwarp();
+        }
+        if (elect_one()) umma_commit(&bar);
+        __syncwarp();
+        mbar_wait(&bar, 0);
+        const long long t1 = clock64();
+        if (blockIdx.x == 0 && (tid & 31) == 0) out[0] = static_cast<unsigned long long>(t1 - t0);
+    } else if (mode == 1 && warp == 1) {
         // converged warp, uniform operands (the 512-column allocation always starts at TMEM address 0), one elected
         // lane issues
         if (tmem != 0) __trap();
@@ -164,6 +194,45 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(unsigned long long* o
         tc_fence_after();
         tmem_dealloc<512>(tmem);
     }
+}
+
+// cp.async.bulk (1-D, TMA engine) global -> shared throughput probe: one converged warp keeps `depth` copies of
+// `bytes` each in flight (ring of depth slots, one mbarrier per slot) for `reps` copies, all CTAs reading the same
+// `span` bytes of `src` (span = bytes * nsrc); out[0] = block 0's cycles.  spin != 0 polls the barrier without the
+// suspend-time hint.
+__global__ void __launch_bounds__(256, 1) bulk_rate_kernel(unsigned long long* out, const uint8_t* __restrict__ src,
+                                                           int bytes, int depth, int reps, int nsrc, int spin) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint64_t bars[8 * 16];
+    const int tid = threadIdx.x, warp = tid >> 5, nwarps = blockDim.x >> 5;
+    if (tid == 0) {
+        for (int i = 0; i < 8 * 16; ++i) mbar_init(&bars[i], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    // every warp runs its own ring of `depth` slots; the warps share the `reps` copies
+    uint64_t* wb = bars + 16 * warp;
+    uint8_t* ws = smem + static_cast<size_t>(warp) * depth * bytes;
+    const int my_reps = reps / nwarps;
+    const long long t0 = clock64();
+    for (int r = 0; r < my_reps + depth; ++r) {
+        const int s = r % depth, u = r / depth;
+        if (u > 0) {                                        // wait for the previous copy into this slot
+            if (spin) { while (!mbar_try_wait(&wb[s], (u - 1) & 1)) {} }
+            else mbar_wait(&wb[s], (u - 1) & 1);
+        }
+        if (r < my_reps) {
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&wb[s], bytes);
+                bulk_g2s(ws + static_cast<size_t>(s) * bytes, src + static_cast<size_t>((r * nwarps + warp) % nsrc) * bytes,
+                         bytes, &wb[s]);
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    const long long t1 = clock64();
+    if (blockIdx.x == 0 && tid == 0) out[0] = static_cast<unsigned long long>(t1 - t0);
 }
 
 }  // namespace sedb

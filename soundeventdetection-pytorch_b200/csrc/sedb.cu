@@ -1,12 +1,17 @@
 // libsedb.so -- C ABI (include/sedb.h) over the hand-written sm_100a kernels.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <map>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/sedb.h"
@@ -64,6 +69,7 @@ struct sedb_ctx {
 };
 
 #include "cnn_host.inl"
+static void sedb_cnn_train_free(sedb_cnn*) {}
 static_assert(sedb::kMelPieceLen == sedb_host::kMelPieceLen && sedb::kMelMaxPieces == sedb_host::kMelMaxPieces,
               "mel piece geometry: kernels and host tables must agree");
 
@@ -94,6 +100,8 @@ int sedb_mel_filterbank(float* out_host) {
     return 0;
 }
 
+int sedb_destroy(sedb_ctx_t* c);
+
 int sedb_create(sedb_ctx_t** out_ctx) {
     if (!out_ctx) return fail("sedb_create: null output");
     *out_ctx = nullptr;
@@ -106,6 +114,10 @@ int sedb_create(sedb_ctx_t** out_ctx) {
                     prop.major, prop.minor);
     sedb_ctx* c = new (std::nothrow) sedb_ctx();
     if (!c) return fail("sedb_create: out of host memory");
+    struct Guard {                                   // a failure below must not leak the partial context
+        sedb_ctx* c;
+        ~Guard() { if (c) sedb_destroy(c); }
+    } guard{c};
     c->device = dev;
     c->num_sms = prop.multiProcessorCount;
     std::vector<uint8_t> a1 = sedb_host::make_stage1_constants(kFp16);
@@ -142,6 +154,7 @@ int sedb_create(sedb_ctx_t** out_ctx) {
     CUDA_TRY(cudaFuncSetAttribute(sedb::power_mel_db_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   80 * 1024));
     if (int rc = sedb_cnn_kernels_init()) return rc;
+    guard.c = nullptr;
     *out_ctx = c;
     return 0;
 }
@@ -395,6 +408,21 @@ int sedb_adam_amsgrad_step(float* param_dev, const float* grad_dev, float* exp_a
     return 0;
 }
 
+int sedb_debug_plan_layer(int cin, int cout, int pool, int mode, int ntaps, int H, int W, int amode, long long n_img,
+                          int num_sms, int* out8) {
+    if (!out8) return fail("null output");
+    UmmaLayer L;
+    L.cin = cin; L.cout = cout; L.pool = pool; L.mode = mode; L.ntaps = ntaps;
+    L.cin_chunk = cin > 128 ? 128 : cin;
+    L.cout_tile = cout > 128 ? 128 : cout;
+    sedb::ConvParams p;
+    const int S = plan_umma_layer(L, H, W, amode, n_img, num_sms, p);
+    if (S < 0) return fail("layer %d->%d at %d x %d cannot be planned", cin, cout, H, W);
+    out8[0] = p.n_tiles; out8[1] = p.n_nsub; out8[2] = p.fuse; out8[3] = p.n_bands; out8[4] = p.R;
+    out8[5] = static_cast<int>(conv_smem_bytes(p)); out8[6] = S; out8[7] = p.kpb * 100 + p.n_wslots * 10 + (p.cstep == 32);
+    return 0;
+}
+
 int sedb_debug_umma_rate(int N, int b_major, int n_acc, int reps, int lbo_a, int lbo_b, int grid,
                          unsigned long long* cycles_host) {
     if (!cycles_host || N < 16 || N > 128 || n_acc < 1 || n_acc > 4 || reps < 1) return fail("bad arguments");
@@ -405,6 +433,26 @@ int sedb_debug_umma_rate(int N, int b_major, int n_acc, int reps, int lbo_a, int
     CUDA_TRY(cudaDeviceSynchronize());
     CUDA_TRY(cudaMemcpy(cycles_host, d, 8, cudaMemcpyDeviceToHost));
     cudaFree(d);
+    return 0;
+}
+
+int sedb_debug_bulk_rate(int bytes, int depth, int reps, int nsrc, int spin, int grid, int nwarps,
+                         unsigned long long* cycles_host) {
+    if (!cycles_host || bytes < 16 || bytes % 16 || depth < 1 || depth > 16 || nwarps < 1 || nwarps > 8 ||
+        bytes * depth * nwarps > 200 * 1024 || reps < 1 || nsrc < 1)
+        return fail("bad arguments");
+    unsigned long long* d = nullptr;
+    uint8_t* src = nullptr;
+    CUDA_TRY(cudaMalloc(&d, 8));
+    CUDA_TRY(cudaMalloc(&src, static_cast<size_t>(bytes) * nsrc));
+    CUDA_TRY(cudaMemset(src, 0, static_cast<size_t>(bytes) * nsrc));
+    CUDA_TRY(cudaFuncSetAttribute(sedb::bulk_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int i = 0; i < 2; ++i)
+        sedb::bulk_rate_kernel<<<grid, 32 * nwarps, bytes * depth * nwarps>>>(d, src, bytes, depth, reps, nsrc, spin);
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(cycles_host, d, 8, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    cudaFree(src);
     return 0;
 }
 

@@ -68,7 +68,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     uint32_t spins = 0;
     long long t0 = 0;
-    while (!mbar_try_wait_hint(bar, parity, 20000u)) {
+#ifndef SEDB_MBAR_HINT_NS
+#define SEDB_MBAR_HINT_NS 20000u
+#endif
+    while (!(SEDB_MBAR_HINT_NS ? mbar_try_wait_hint(bar, parity, SEDB_MBAR_HINT_NS) : mbar_try_wait(bar, parity))) {
         if ((++spins & 0xffu) == 0) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
@@ -166,6 +169,21 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// The same with the descriptors given as (lo, hi) words: only the start-address field (low 14 bits of lo) differs
+// between the operands of a kernel, so the issuing thread does 32-bit adds on lo and keeps hi constant.  The single
+// issuing thread is instruction-latency bound (a handful of dependent uniform-datapath instructions cost as much as a
+// narrow MMA takes to run: tests/dev/umma_switch.py), so every instruction per MMA counts.
+__device__ __forceinline__ void umma_f16_lh(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem]: the A operand (M = 128 lanes, 16-bit elements, two consecutive K per 32-bit column,

@@ -15,8 +15,8 @@ def _ptr(t):
 class NativeHandle:
     """Owns a sedb_cnn_t / sedb_m5_t for one CUDA device and keeps it in sync with the module's tensors."""
 
-    def __init__(self, create, destroy, load):
-        self._create, self._destroy, self._load = create, destroy, load
+    def __init__(self, create, destroy, load, invalidate=None):
+        self._create, self._destroy, self._load, self._invalidate = create, destroy, load, invalidate
         self._handles = {}       # device index -> (handle, parameter fingerprint)
         self._workspaces = {}    # (device, key) -> uint8 tensor
 
@@ -43,6 +43,11 @@ class NativeHandle:
         ws = self._workspaces.get(k)
         if ws is None or ws.numel() < nbytes:
             self._workspaces.clear()                             # keep at most one live workspace per module
+            # the library remembers which (pointer, geometry) it has zeroed the padding of; memory handed back by the
+            # caching allocator may have been scribbled on since, so forget everything it knew
+            if self._invalidate is not None:
+                for h, _ in self._handles.values():
+                    self._invalidate(h, None)
             ws = torch.empty(nbytes + 128, dtype=torch.uint8, device=device)
             self._workspaces[k] = ws
         return ws

@@ -117,7 +117,7 @@ class Cnn_AvgPooling(nn.Module):
             def load(h, arr, cnt):
                 _ext.check(lib.sedb_cnn_load(h, arr, cnt, _ext.stream_ptr()))
 
-            self._native = NativeHandle(create, lib.sedb_cnn_destroy, load)
+            self._native = NativeHandle(create, lib.sedb_cnn_destroy, load, lib.sedb_cnn_workspace_invalidate)
         return self._native.get(device, self._native_tensors())
 
     def _forward_native(self, x, want_probs):

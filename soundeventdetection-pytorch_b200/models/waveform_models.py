@@ -66,7 +66,7 @@ class M5(nn.Module):
             def load(h, arr, cnt):
                 _ext.check(lib.sedb_m5_load(h, arr, cnt, _ext.stream_ptr()))
 
-            self._native = NativeHandle(create, lib.sedb_m5_destroy, load)
+            self._native = NativeHandle(create, lib.sedb_m5_destroy, load, lib.sedb_m5_workspace_invalidate)
         return self._native.get(device, self._native_tensors())
 
     def _forward_native(self, x):

@@ -15,8 +15,8 @@ lib.sedb_debug_phase_profile(1, None)
 m.logits(x); torch.cuda.synchronize()
 out = np.zeros(128, dtype=np.uint64)
 lib.sedb_debug_phase_profile(0, ctypes.c_void_p(out.ctypes.data))
-names = ["epi wait", "epi work", "mma wait patch", "mma issue+wait W", "mma wait tmem", "copy wait patch_free"]
+names = ["epi wait", "epi work", "mma wait patch", "mma issue", "mma wait tmem", "copy wait patch_free", "items", "mma wait W"]
 for L in range(7):
     c = out[16 * (L + 1): 16 * (L + 2)]
     items = max(1, int(c[6]))
-    print(f"layer {L}: items/CTA-thread0 {items}", " | ".join(f"{n} {int(v)//items}" for n, v in zip(names, c[:6])))
+    print(f"layer {L}: items/CTA-thread0 {items}", " | ".join(f"{n} {int(v)//items}" for n, v in zip(names, c[:8])))
