@@ -116,6 +116,34 @@ int sedb_cnn_workspace_invalidate(sedb_cnn_t* cnn, const void* workspace_dev);
 int sedb_cnn_forward(sedb_cnn_t* cnn, const float* x_dev, long long n_clips, long long T, float* logits_dev,
                      float* probs_dev, void* workspace_dev, size_t workspace_bytes, void* stream);
 
+/* ---- training step of Cnn_AvgPooling (train.py:96-103) -------------------------------------------------------------
+ * Replaces `model.train(); out = model(x); loss = criterion(out, y); loss.backward()` for the spectrogram CNN:
+ * train-mode forward with batch-statistics BatchNorm (models/spectogram_models.py:153-160; eps 1e-5, running
+ * statistics updated in place with `momentum`, unbiased variance -- torch.nn.BatchNorm2d defaults), then the backward
+ * pass from dL/dlogits to every parameter gradient.  Convolutions (forward, data gradient, weight gradient) run on
+ * tcgen05 with bf16 hi+lo split operands and fp32 accumulation; BN statistics are accumulated in fp64.
+ * tensors_dev: the same list as sedb_cnn_load (conv weights, BN weight/bias/running_mean/running_var, event_fc), read
+ * directly -- no load step; running_mean / running_var are written.
+ * The workspace (sedb_cnn_train_workspace_bytes) carries the forward activations to the backward call: call backward
+ * with the same workspace, shape and x_dev, before the next forward.  Same zero-padding contract as
+ * sedb_cnn_forward (sedb_cnn_workspace_invalidate also forgets training workspaces). */
+size_t sedb_cnn_train_workspace_bytes(sedb_cnn_t* cnn, long long n_clips, long long T);
+int sedb_cnn_train_forward(sedb_cnn_t* cnn, float* const* tensors_dev, int n_tensors, const float* x_dev,
+                           long long n_clips, long long T, float momentum, float* logits_dev, void* workspace_dev,
+                           size_t workspace_bytes, void* stream);
+/* dlogits_dev: [n_clips, out_frames, classes] = dL/d(forward output).  grads_dev: one float32 buffer per parameter in
+ * module.parameters() order -- per block conv1.weight, conv2.weight, bn1.weight, bn1.bias, bn2.weight, bn2.bias, then
+ * event_fc.weight, event_fc.bias -- each OVERWRITTEN with the gradient (they may be views of one flat bucket). */
+int sedb_cnn_train_backward(sedb_cnn_t* cnn, float* const* tensors_dev, int n_tensors, const float* x_dev,
+                            const float* dlogits_dev, long long n_clips, long long T, float* const* grads_dev,
+                            int n_grads, void* workspace_dev, size_t workspace_bytes, void* stream);
+/* WeightedBCE (utils/common.py:11-30, multi_frame=True): binary_cross_entropy_with_logits(output[:, :N],
+ * target[:, :N], pos_weight) with N = min(F_out, F_tgt), mean reduction.  loss_dev[0] receives the loss, dlogits_dev
+ * ([B, F_out, K], nullable) grad_scale * dloss/doutput (zero beyond frame N).  Either output may be NULL. */
+int sedb_bce_with_logits(const float* logits_dev, const float* target_dev, long long B, long long F_out,
+                         long long F_tgt, int K, float pos_weight, float grad_scale, float* loss_dev,
+                         float* dlogits_dev, void* stream);
+
 /* ---- waveform CNN: M5 (models/waveform_models.py:9-71) ------------------------------------------ */
 int sedb_m5_create(sedb_ctx_t* ctx, int classes_num, sedb_m5_t** out);
 int sedb_m5_destroy(sedb_m5_t* m5);
@@ -139,6 +167,14 @@ int sedb_adam_amsgrad_step(float* param_dev, const float* grad_dev, float* exp_a
                            float* max_exp_avg_sq_dev, long long n, float lr, float beta1, float beta2, float eps,
                            float weight_decay, long long step, float grad_scale, void* stream);
 
+/* The same update with the step counter and the learning rate in device memory, so that a captured CUDA graph of the
+ * whole training step can be replayed: state_dev[0] = number of steps done so far (float, incremented by the call),
+ * state_dev[1] = lr (train.py:108-110 decays it on the host every 200 iterations: write the new value there);
+ * hyper_dev: 2 floats of scratch. */
+int sedb_adam_amsgrad_step_dev(float* param_dev, const float* grad_dev, float* exp_avg_dev, float* exp_avg_sq_dev,
+                               float* max_exp_avg_sq_dev, long long n, float* state_dev, float* hyper_dev, float beta1,
+                               float beta2, float eps, float weight_decay, float grad_scale, void* stream);
+
 /* ---- end-to-end: waveform -> log-mel -> CNN -> frame probabilities -------------------------------- */
 /* infer.py:27-33 intent.  wave_host: [n_clips, wave_stride] float32 host; probs_host: [n_clips, out_frames,
  * classes] float32 host.  H2D chunks, log-mel, CNN and the D2H of the probabilities are pipelined. */
@@ -157,6 +193,10 @@ int sedb_sed_host_pcm16(sedb_ctx_t* ctx, sedb_cnn_t* cnn, const int16_t* pcm_hos
  * stride; neg_b: set the B-negate bit. */
 int sedb_debug_umma_probe(const float* a_dev, const float* b_dev, float* d_dev, int N, int K, int a_major,
                           int b_major, int pad, int neg_b, int swap_lbo_sbo, void* stream);
+/* Workspace layout of the training step for (n_clips, T): out = {layers, G offset, partial-sum offset, bytes} then per
+ * conv layer {C_out, H, W, pool, Z offset, Z plane pixels, A offset, A plane pixels, dZ offset, dZ plane pixels, offset of
+ * the statistics (in doubles), weight-gradient chunks * 1000 + band pixels}.  Used by the tests to compare intermediates. */
+int sedb_debug_train_layout(sedb_cnn_t* cnn, long long n_clips, long long T, long long* out, int max_out);
 /* Host-only: the decomposition the planner picks for one tensor-core conv layer (cin -> cout, pool, mode 0 = 3x3 2-D /
  * 1 = k3 1-D, input H x W, amode 0 = inference fp16 / 1 = training bf16 split) over n_img images on num_sms SMs.
  * out8 = {M tiles per item, N sub-items, fused [wH|wL] MMA, bands per image, rows per band, smem bytes, input plane

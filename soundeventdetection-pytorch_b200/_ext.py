@@ -49,6 +49,17 @@ _SIGNATURES = {
                                         ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "sedb_cnn_workspace_invalidate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "sedb_m5_workspace_invalidate": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "sedb_cnn_train_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p, c_ll, c_ll]),
+    "sedb_cnn_train_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, c_float_p,
+                                              c_ll, c_ll, ctypes.c_float, c_float_p, ctypes.c_void_p, ctypes.c_size_t,
+                                              ctypes.c_void_p]),
+    "sedb_cnn_train_backward": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int, c_float_p,
+                                               c_float_p, c_ll, c_ll, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
+                                               ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "sedb_bce_with_logits": (ctypes.c_int, [c_float_p, c_float_p, c_ll, c_ll, c_ll, ctypes.c_int, ctypes.c_float,
+                                            ctypes.c_float, c_float_p, c_float_p, ctypes.c_void_p]),
+    "sedb_adam_amsgrad_step_dev": (ctypes.c_int, [c_float_p] * 5 + [c_ll, c_float_p, c_float_p] + [ctypes.c_float] * 5
+                                   + [ctypes.c_void_p]),
     "sedb_m5_create": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "sedb_m5_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "sedb_m5_load": (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_void_p), ctypes.c_int,
@@ -62,6 +73,7 @@ _SIGNATURES = {
                                          c_float_p]),
     "sedb_debug_umma_probe": (ctypes.c_int, [c_float_p, c_float_p, c_float_p] + [ctypes.c_int] * 7
                               + [ctypes.c_void_p]),
+    "sedb_debug_train_layout": (ctypes.c_int, [ctypes.c_void_p, c_ll, c_ll, ctypes.POINTER(c_ll), ctypes.c_int]),
     "sedb_debug_plan_layer": (ctypes.c_int, [ctypes.c_int] * 8 + [c_ll, ctypes.c_int, ctypes.POINTER(ctypes.c_int)]),
     "sedb_debug_umma_rate": (ctypes.c_int, [ctypes.c_int] * 7 + [ctypes.c_void_p]),
     "sedb_debug_bulk_rate": (ctypes.c_int, [ctypes.c_int] * 7 + [ctypes.c_void_p]),

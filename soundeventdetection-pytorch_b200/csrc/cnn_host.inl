@@ -356,6 +356,7 @@ static int sedb_cnn_kernels_init() {
 }
 
 static void sedb_cnn_train_free(sedb_cnn* m);
+static void sedb_cnn_train_invalidate(sedb_cnn* m, const void* ws);
 
 extern "C" {
 
@@ -477,6 +478,7 @@ size_t sedb_cnn_workspace_bytes(const sedb_cnn_t* m, long long n_clips, long lon
 int sedb_cnn_workspace_invalidate(sedb_cnn_t* m, const void* workspace_dev) {
     if (!m) return fail("sedb_cnn_workspace_invalidate: null handle");
     m->zeroed.drop(workspace_dev);
+    sedb_cnn_train_invalidate(m, workspace_dev);
     return 0;
 }
 

@@ -19,6 +19,7 @@
 #include "logmel.cuh"
 #include "probe.cuh"
 #include "cnn.cuh"
+#include "cnn_train.cuh"
 
 namespace {
 
@@ -69,7 +70,7 @@ struct sedb_ctx {
 };
 
 #include "cnn_host.inl"
-static void sedb_cnn_train_free(sedb_cnn*) {}
+#include "cnn_train_host.inl"
 static_assert(sedb::kMelPieceLen == sedb_host::kMelPieceLen && sedb::kMelMaxPieces == sedb_host::kMelMaxPieces,
               "mel piece geometry: kernels and host tables must agree");
 

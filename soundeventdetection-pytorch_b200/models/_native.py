@@ -42,7 +42,10 @@ class NativeHandle:
         k = (device.index, key)
         ws = self._workspaces.get(k)
         if ws is None or ws.numel() < nbytes:
-            self._workspaces.clear()                             # keep at most one live workspace per module
+            kind = key[0] == "train" if isinstance(key, tuple) and key else False
+            # keep at most one live workspace per kind (inference / training) and module
+            for old in [q for q in self._workspaces if (isinstance(q[1], tuple) and q[1] and q[1][0] == "train") == kind]:
+                del self._workspaces[old]
             # the library remembers which (pointer, geometry) it has zeroed the padding of; memory handed back by the
             # caching allocator may have been scribbled on since, so forget everything it knew
             if self._invalidate is not None:
@@ -63,6 +66,14 @@ class NativeHandle:
 
     def __del__(self):
         self.close()
+
+    # a handle is device state of ONE module object: copies and pickles of the module start without it and rebuild it
+    # lazily on their first forward (ctypes pointers cannot be pickled, and two owners would double-free)
+    def __deepcopy__(self, memo):
+        return None
+
+    def __reduce__(self):
+        return (type(None), ())
 
 
 def aligned_ptr(ws: torch.Tensor):

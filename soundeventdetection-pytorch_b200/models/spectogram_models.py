@@ -7,8 +7,12 @@ reference's ``train.py:123-128`` load unchanged and ``main.py:35`` / ``infer.py:
 * eval mode (``model.eval()``; what ``train.py:21-24`` and ``infer.py:32-33`` run): ``forward``/``logits`` execute the
   hand-written sm_100a kernels of libsedb.so (implicit-GEMM tcgen05 convolutions with folded BatchNorm, fused
   head).  CUDA only -- a CPU tensor raises, there is no fallback.
-* train mode: ``forward`` is expressed with differentiable torch ops so ``train.py:96-103`` keeps working; the native
-  backward kernels are not part of this round.
+* train mode on a CUDA tensor (``train.py:96-103``): ``forward`` is ONE autograd node backed by the native training
+  kernels of libsedb.so -- batch-statistics BatchNorm forward (running statistics updated in place), and in
+  ``backward`` the BN / ReLU / pooling / head gradients plus tcgen05 data- and weight-gradient convolutions -- so the
+  reference loop ``loss = criterion(model(x), y); loss.backward(); optimizer.step()`` runs on them unchanged.  The input
+  is treated as data (no gradient w.r.t. ``x``).  On CPU tensors, or with ``model.native_training = False``, train mode
+  falls back to the differentiable torch expression of the same network (used by the CPU tests as the comparison).
 """
 from __future__ import annotations
 
@@ -78,7 +82,26 @@ class ConvBlock(nn.Module):
         return F.avg_pool2d(x, kernel_size=self.pool_size)
 
 
+class _NativeTrainFunction(torch.autograd.Function):
+    """forward: sedb_cnn_train_forward; backward: sedb_cnn_train_backward (include/sedb.h).  The activations live in
+    the module's training workspace between the two calls, as in one iteration of train.py:96-103."""
+
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        ctx.module, ctx.x = module, x
+        ctx.token = module._train_forward_native(x)
+        ctx.mark_non_differentiable()
+        return module._train_out
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        grads = ctx.module._train_backward_native(ctx.x, dlogits.contiguous(), ctx.token)
+        return (None, None) + tuple(grads)
+
+
 class Cnn_AvgPooling(nn.Module):
+    native_training = True       # train-mode forward/backward of CUDA tensors on the native kernels
+
     def __init__(self, classes_num, model_config=DEFAULT_CHANNEL_AND_POOL):
         super().__init__()
         self.model_config = model_config
@@ -104,7 +127,7 @@ class Cnn_AvgPooling(nn.Module):
             ts += blk.native_tensors()
         return ts + [self.event_fc.weight, self.event_fc.bias]
 
-    def _handle(self, device):
+    def _handle_init(self):
         lib = _ext.load()
         if self._native is None:
             channels = (ctypes.c_int * len(self.model_config))(*[int(c) for c, _ in self.model_config])
@@ -118,6 +141,9 @@ class Cnn_AvgPooling(nn.Module):
                 _ext.check(lib.sedb_cnn_load(h, arr, cnt, _ext.stream_ptr()))
 
             self._native = NativeHandle(create, lib.sedb_cnn_destroy, load, lib.sedb_cnn_workspace_invalidate)
+
+    def _handle(self, device):
+        self._handle_init()
         return self._native.get(device, self._native_tensors())
 
     def _forward_native(self, x, want_probs):
@@ -144,12 +170,96 @@ class Cnn_AvgPooling(nn.Module):
                                             _ptr(out) if want_probs else None, ws_ptr, ws_bytes, _ext.stream_ptr()))
         return out
 
+    # ------------------------------------------------------------------ native training step
+    def _train_params(self):
+        """module.parameters() order: the order of the gradient list of sedb_cnn_train_backward."""
+        ps = []
+        for blk in self.conv_blocks:
+            ps += [blk.conv1.weight, blk.conv2.weight, blk.bn1.weight, blk.bn1.bias, blk.bn2.weight, blk.bn2.bias]
+        return ps + [self.event_fc.weight, self.event_fc.bias]
+
+    def _train_handle(self, device):
+        """The native handle WITHOUT (re)loading folded inference weights: the training entry points read the tensors."""
+        self._handle_init()
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        entry = self._native._handles.get(idx)
+        if entry is None:
+            h = ctypes.c_void_p()
+            self._native._create(ctypes.byref(h))
+            entry = [h, None]
+            self._native._handles[idx] = entry
+        return entry[0]
+
+    def _tensor_array(self, tensors):
+        for t in tensors:
+            if t.dtype != torch.float32 or not t.is_contiguous() or not t.is_cuda:
+                raise RuntimeError("native training needs contiguous float32 CUDA parameters and buffers")
+        return (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+
+    def _train_forward_native(self, x):
+        lib = _ext.load()
+        if x.dim() != 4 or x.shape[1] != audio_channels or x.shape[3] != mel_bins:
+            raise ValueError(f"expected input (batch, {audio_channels}, time_steps, {mel_bins}), got {tuple(x.shape)}")
+        B, _, T, _ = x.shape
+        with torch.cuda.device(x.device):
+            h = self._train_handle(x.device)
+            out_frames = lib.sedb_cnn_out_frames(h, T)
+            if out_frames <= 0 or B == 0:
+                raise ValueError(f"native training needs a non-empty batch of at least {2 ** self.num_pools} frames")
+            need = lib.sedb_cnn_train_workspace_bytes(h, B, T)
+            if need == 0:
+                raise _ext.SedbError(lib.sedb_last_error().decode())
+            ws = self._native.workspace(x.device, ("train", B, T), need)
+            ws_ptr, ws_bytes = aligned_ptr(ws)
+            self._train_out = torch.empty((B, out_frames, self.classes_num), dtype=torch.float32, device=x.device)
+            tensors = self._native_tensors()
+            momentum = self.conv_blocks[0].bn1.momentum
+            _ext.check(lib.sedb_cnn_train_forward(h, self._tensor_array(tensors), len(tensors), _ptr(x), B, T,
+                                                  0.1 if momentum is None else float(momentum), _ptr(self._train_out),
+                                                  ws_ptr, ws_bytes, _ext.stream_ptr()))
+            # bookkeeping torch would have done: num_batches_tracked, and the version of the buffers written behind its back
+            bns = [bn for blk in self.conv_blocks for bn in (blk.bn1, blk.bn2)]
+            torch._foreach_add_([bn.num_batches_tracked for bn in bns], 1)
+            bump = torch.autograd.graph.increment_version
+            for bn in bns:
+                bump(bn.running_mean)
+                bump(bn.running_var)
+        self._train_token = getattr(self, "_train_token", 0) + 1
+        return self._train_token
+
+    def _train_backward_native(self, x, dlogits, token):
+        if token != self._train_token:
+            raise RuntimeError("native training keeps the activations of ONE forward pass: call backward before the next "
+                               "train-mode forward (train.py:96-103 does)")
+        lib = _ext.load()
+        B, _, T, _ = x.shape
+        params = self._train_params()
+        grads = [torch.empty_like(p) for p in params]
+        with torch.cuda.device(x.device):
+            h = self._train_handle(x.device)
+            ws = self._native.workspace(x.device, ("train", B, T), 0)
+            ws_ptr, ws_bytes = aligned_ptr(ws)
+            tensors = self._native_tensors()
+            _ext.check(lib.sedb_cnn_train_backward(h, self._tensor_array(tensors), len(tensors), _ptr(x), _ptr(dlogits), B,
+                                                   T, self._tensor_array(grads), len(grads), ws_ptr, ws_bytes,
+                                                   _ext.stream_ptr()))
+        return grads
+
+    def _use_native_training(self, x):
+        return (self.native_training and x.is_cuda and torch.is_grad_enabled()
+                and all(p.requires_grad for p in self._train_params()))
+
     # ------------------------------------------------------------------ reference interface
     def forward(self, x):
         """Input (batch, channels, time_steps, freq_bins) -> frame logits (batch, time_steps', classes)."""
         if not self.training:
             with torch.no_grad():
                 return self._forward_native(x, want_probs=False)
+        if self._use_native_training(x):
+            if x.requires_grad:
+                raise NotImplementedError("the native training path treats the input as data (no gradient w.r.t. x); set "
+                                          "model.native_training = False for that")
+            return _NativeTrainFunction.apply(self, x.detach().to(torch.float32).contiguous(), *self._train_params())
         x = self.conv_blocks(x)
         x = torch.mean(x, dim=3).transpose(1, 2)
         return interpolate(self.event_fc(x), 2 ** self.num_pools)
