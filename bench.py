@@ -13,6 +13,10 @@ Prints ONE JSON line (rank 0).  Keys beyond the base contract:
   tensor        executed tensor-core FLOPs of the same kernel vs the measured bf16 peak (the MMAs run at their floor; the rest is operand production)
   cpu_baseline  the oracle port of the reference CPU path timed on this box's host cores on a bounded sample
   e2e           same metric through the C-ABI host-buffer entry point (pinned host memory, H2D + D2H inside the timing)
+  config3       BASELINE config 3: Cnn_AvgPooling frame inference, 128 clips IN TOTAL split 128/N over the ranks (strong scaling)
+  config4       BASELINE config 4: one training step per GPU on 64 ten-second crops (fused log-mel + native train-mode
+                forward / WeightedBCE / backward + ONE NCCL all-reduce + fused Adam-amsgrad), whole step in a CUDA graph
+  config5       BASELINE config 5: M5 on raw waveform frames, 128 frames in total split over the ranks, plus a 1024-frame point
 """
 from __future__ import annotations
 
@@ -198,6 +202,164 @@ def run_reference(args):
     emit(line)
 
 
+
+# ------------------------------------------------------------------------------------------------- other BASELINE configs
+M5_FLOP_PER_FRAME = 237_570_560
+TRAIN_FLOP_PER_CROP = 3 * 153_281_280   # forward + data gradient + weight gradient of the T = 30 crop
+
+
+def _timed(fn, steps, warmup, dev, sync_ranks=True):
+    """CUDA-event time per call (ms), max over ranks."""
+    import torch
+    from sed_b200 import parallel
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if sync_ranks:
+        parallel.barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    return parallel.max_over_ranks(ms, dev) if sync_ranks else ms
+
+
+def bench_config3(model, dev, rank, world, steps, tf_peak):
+    """128 clips in total, sharded by clip over the ranks; log-mel images resident in HBM; CNN forward only."""
+    import torch
+    from sed_b200 import parallel
+    total = 128
+    lo, hi = parallel.shard_range(total, rank, world)
+    n = hi - lo
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    x = torch.randn(max(n, 1), 1, FRAMES, 64, device=dev, generator=g)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)            # > L2: evicts activations between calls
+
+    def fwd():
+        if n > 0:
+            with torch.no_grad():
+                model.logits(x[:n])
+
+    def fwd_flushed():
+        flush.zero_()
+        fwd()
+
+    ms = _timed(fwd, max(steps, 20), 5, dev)
+    ms_fl = _timed(fwd_flushed, 10, 2, dev) - _timed(lambda: flush.zero_(), 10, 2, dev)
+    tfl = total * CNN_FLOP_PER_CLIP / (ms * 1e-3) / 1e12
+    return {"workload": f"{total} x 60 s clips in total, {n} on rank 0: Cnn_AvgPooling(32-64-128-128) frame probabilities, "
+                        f"log-mel input resident in HBM", "clips_total": total, "scaling": "strong",
+            "ms_per_step": ms, "ms_per_step_l2_flushed": ms_fl,
+            "audio_hours_per_sec": total * CLIP_SECONDS / 3600.0 / (ms * 1e-3),
+            "roofline": {"bound": "tensor", "achieved": tfl, "peak": tf_peak * world, "unit": "TFLOP/s",
+                         "frac": tfl / (tf_peak * world),
+                         "note": "algorithmic FLOPs (965.77 MFLOP/clip); the kernels execute 2 MMAs per product "
+                                 "(fp16 activations x fp16 hi+lo weights)"}}
+
+
+def bench_config5(dev, rank, world, steps, tf_peak):
+    import torch
+    import refmodels
+    from sed_b200 import parallel
+    m5, _ = refmodels.seeded_m5()
+    m5 = m5.to(dev).eval()
+    out = {}
+    for total in (128, 1024):
+        lo, hi = parallel.shard_range(total, rank, world)
+        n = hi - lo
+        g = torch.Generator(device=dev).manual_seed(99 + rank)
+        x = torch.randn(max(n, 1), 1, 31680, device=dev, generator=g) * 0.1
+
+        def fwd():
+            if n > 0:
+                with torch.no_grad():
+                    m5(x[:n])
+
+        ms = _timed(fwd, max(steps, 20), 5, dev)
+        tfl = total * M5_FLOP_PER_FRAME / (ms * 1e-3) / 1e12
+        out[f"frames_{total}"] = {"ms_per_step": ms, "frames_per_sec": total / (ms * 1e-3),
+                                  "audio_hours_per_sec": total / (ms * 1e-3) * 0.33 / 3600.0,
+                                  "roofline": {"bound": "tensor", "achieved": tfl, "peak": tf_peak * world, "unit": "TFLOP/s",
+                                               "frac": tfl / (tf_peak * world)}}
+    out["workload"] = "M5 (models/waveform_models.py) on raw 0.66 s frames [n, 1, 31680], frames split over the ranks"
+    out["scaling"] = "strong"
+    return out
+
+
+def bench_config4(dev, rank, world, steps, tf_peak):
+    """One data-parallel training step per GPU: 64 crops x 10 s -> fused log-mel -> native train step (graph)."""
+    import torch
+    import torch.distributed as dist
+    from sed_b200 import parallel
+    from sed_b200.dataset.spectogram import preprocess as P
+    from sed_b200.models.spectogram_models import Cnn_AvgPooling
+    from sed_b200.train import DataParallelTrainer, allreduce_sum_
+    from sed_b200.utils.common import WeightedBCE
+    import refmodels
+    torch.manual_seed(0)
+    model = Cnn_AvgPooling(1, model_config=refmodels.MAIN_CFG).to(dev)
+    crit = WeightedBCE(recall_factor=5, multi_frame=True)
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    wave = (torch.randn(64, 480000, device=dev, generator=g) * 0.1).clamp_(-1, 1)
+    target = (torch.rand(64, 30, 1, device=dev, generator=g) > 0.8).float()
+    mean = torch.full((64,), 18.0, device=dev)
+    std = torch.full((64,), 6.0, device=dev)
+    tr = DataParallelTrainer(model, crit, lr=1e-6, graph=True)
+
+    def step():
+        x = P.waveform_to_log_mel(wave, mean=mean, std=std)[:, None, :30].contiguous()
+        return tr.step(x, target)
+
+    ms = _timed(step, max(steps, 20), 5, dev)
+    loss = float(step())
+    # the split, eagerly (no graph), with events between the stages
+    tr2 = DataParallelTrainer(model, crit, lr=1e-6, graph=False)
+    names = ("logmel", "forward", "loss", "backward", "allreduce", "update")
+    acc = {k: 0.0 for k in names}
+    reps = 10
+    from sed_b200 import _ext
+    import ctypes
+    lib = _ext.load()
+    for it in range(reps + 3):
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(7)]
+        e[0].record()
+        x = P.waveform_to_log_mel(wave, mean=mean, std=std)[:, None, :30].contiguous()
+        e[1].record()
+        model.train()
+        model._train_forward_native(x)
+        e[2].record()
+        out = model._train_out
+        dl = torch.empty_like(out)
+        p = lambda t: ctypes.c_void_p(t.data_ptr())    # noqa: E731
+        _ext.check(lib.sedb_bce_with_logits(p(out), p(target), 64, out.shape[1], 30, 1, 5.0, 1.0, p(tr2._loss), p(dl),
+                                            _ext.stream_ptr()))
+        e[3].record()
+        grads = model._train_backward_native(x, dl, model._train_token)
+        e[4].record()
+        allreduce_sum_(tr2.flat.grad)
+        e[5].record()
+        tr2._apply_update_dev()
+        e[6].record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            for k, a, b in zip(names, e[:-1], e[1:]):
+                acc[k] += a.elapsed_time(b) / reps
+        del grads
+    tfl = world * 64 * TRAIN_FLOP_PER_CROP / (ms * 1e-3) / 1e12
+    return {"workload": "per GPU: 64 waveform crops x 10 s -> fused log-mel -> Cnn_AvgPooling(32-64-128-128) train-mode "
+                        "forward (batch-stat BN) + WeightedBCE(5) + backward (native tcgen05 dgrad/wgrad) + one NCCL "
+                        "all-reduce of the 2.33 MB bucket + fused Adam-amsgrad; whole step replayed as a CUDA graph",
+            "crops_per_gpu": 64, "scaling": "weak", "ms_per_step": ms, "steps_per_sec": 1e3 / ms,
+            "audio_hours_per_sec": world * 64 * 10.0 / 3600.0 / (ms * 1e-3), "loss": loss,
+            "split_ms_eager": acc,
+            "roofline": {"bound": "tensor", "achieved": tfl, "peak": tf_peak * world, "unit": "TFLOP/s",
+                         "frac": tfl / (tf_peak * world),
+                         "note": "algorithmic FLOPs 3 x 153.28 MFLOP per crop; launch/latency-bound at this size"}}
+
+
 # ------------------------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import numpy as np
@@ -329,9 +491,18 @@ def run_ours(args):
                          "ms_per_step": pcm_ms, "h2d_bytes_per_step": Ce * CLIP_SAMPLES * 2 + 512,
                          "d2h_bytes_per_step": Ce * 176 * 4, "clips_per_step": Ce}}
 
+    # ---- the other BASELINE configurations (every rank takes part: sharding, all-reduce), reported in the same line
+    hbm_peak, tf_peak, src = measured_peaks()
+    del wave, host_wave
+    torch.cuda.empty_cache()
+    extra = {}
+    if not args.no_configs:
+        extra["config3"] = bench_config3(model, dev, rank, world, args.steps, tf_peak)
+        extra["config5"] = bench_config5(dev, rank, world, args.steps, tf_peak)
+        extra["config4"] = bench_config4(dev, rank, world, args.steps, tf_peak)
+
     if rank != 0:
         return
-    hbm_peak, tf_peak, src = measured_peaks()
     achieved = C * ALGO_BYTES_PER_CLIP / (lm_ms * 1e-3) / 1e9
     tflops = C * FRAMES * LOGMEL_MMA_FLOP_PER_FRAME / (lm_ms * 1e-3) / 1e12
     line = {
@@ -357,6 +528,7 @@ def run_ours(args):
     }
     if pcm16 is not None:
         line["pcm16"] = pcm16
+    line.update(extra)
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
     emit(line)
@@ -392,6 +564,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pcm16", action="store_true", help="skip the 16-bit PCM variant of the measurement")
+    ap.add_argument("--no-configs", action="store_true", help="skip the config3 / config4 / config5 sub-measurements")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -20,6 +20,12 @@ class NativeHandle:
         self._handles = {}       # device index -> (handle, parameter fingerprint)
         self._workspaces = {}    # (device, key) -> uint8 tensor
 
+    def mark_dirty(self):
+        """Forget the parameter fingerprints: the next get() repacks.  Called when the module enters or leaves train mode
+        (a torch train-mode forward updates BatchNorm running statistics without bumping their version counter)."""
+        for entry in self._handles.values():
+            entry[1] = None
+
     def get(self, device: torch.device, tensors):
         """Returns the handle for `device`, (re)loading parameters when any tensor changed since the last call."""
         idx = device.index if device.index is not None else torch.cuda.current_device()

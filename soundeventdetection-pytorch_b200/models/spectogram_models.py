@@ -249,6 +249,11 @@ class Cnn_AvgPooling(nn.Module):
         return (self.native_training and x.is_cuda and torch.is_grad_enabled()
                 and all(p.requires_grad for p in self._train_params()))
 
+    def train(self, mode: bool = True):
+        if self._native is not None and mode != self.training:
+            self._native.mark_dirty()         # BatchNorm statistics may change behind the version counters
+        return super().train(mode)
+
     # ------------------------------------------------------------------ reference interface
     def forward(self, x):
         """Input (batch, channels, time_steps, freq_bins) -> frame logits (batch, time_steps', classes)."""

@@ -88,6 +88,11 @@ class M5(nn.Module):
             _ext.check(lib.sedb_m5_forward(h, _ptr(x), n, _ptr(out), ws_ptr, ws_bytes, _ext.stream_ptr()))
         return out
 
+    def train(self, mode: bool = True):
+        if self._native is not None and mode != self.training:
+            self._native.mark_dirty()         # BatchNorm statistics may change behind the version counters
+        return super().train(mode)
+
     def forward(self, x):
         # x: (b, c, frame_size) -> (b, classes) logits
         if not self.training:

@@ -2,6 +2,7 @@
 trainer reproduce torch.optim.Adam(amsgrad=True) as constructed at the reference's train.py:85."""
 import copy
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -99,3 +100,76 @@ def test_native_handle_sees_fused_updates_without_a_train_forward():
     ref = torch.sigmoid(cnn_ref.cnn_avgpooling_forward(sd, x.cpu(), [p for _, p in refmodels.MAIN_CFG]))
     assert (y1 - y0).abs().max() > 1e-3                 # the update is visible ...
     assert (y1.cpu() - ref).abs().max() < 1e-3          # ... and it is exactly the updated model
+
+
+def test_trainer_graph_replay_equals_eager_and_checkpoint_roundtrip(tmp_path):
+    """The captured CUDA graph of the whole iteration (native forward / loss / backward / update) replays to the same
+    parameters as eager execution; the optimizer state loads into torch.optim.Adam(amsgrad=True) (train.py:85,123-128)."""
+    crit = WeightedBCE(recall_factor=5, multi_frame=True)
+    models, trainers = [], []
+    for graph in (False, True):
+        m, _ = refmodels.seeded_cnn(refmodels.MAIN_CFG)
+        m = m.cuda()
+        models.append(m)
+        trainers.append(DataParallelTrainer(m, crit, lr=1e-3, graph=graph))
+    losses = [[], []]
+    for it in range(4):
+        x = refmodels.cnn_inputs(30, 700 + it, batch=8).cuda()
+        y = (torch.rand(8, 30, 1, generator=torch.Generator().manual_seed(it)) > 0.8).float().cuda()
+        for k, tr in enumerate(trainers):
+            losses[k].append(float(tr.step(x, y)))
+        if it == 1:
+            for tr in trainers:
+                tr.decay_lr(0.5)                           # the device-resident learning rate follows
+    assert np.allclose(losses[0], losses[1], rtol=1e-5)
+    for (n, p), (_, q) in zip(models[0].named_parameters(), models[1].named_parameters()):
+        assert torch.allclose(p, q, atol=2e-6, rtol=1e-4), n
+    for (n, p), (_, q) in zip(models[0].named_buffers(), models[1].named_buffers()):
+        assert torch.allclose(p.float(), q.float(), atol=1e-5, rtol=1e-4), n
+    assert trainers[1].step_count == 4 and abs(trainers[1].lr - 5e-4) < 1e-12
+    # checkpoint in the reference's format; the optimizer part loads into torch's Adam
+    ck = {"iterations": 4, "model": models[1].state_dict(), "optimizer": trainers[1].state_dict()}
+    path = os.path.join(tmp_path, "iteration_4.pth")
+    torch.save(ck, path)
+    ck2 = torch.load(path, weights_only=False)
+    ref_model, _ = refmodels.seeded_cnn(refmodels.MAIN_CFG)
+    ref_model = ref_model.cuda()
+    ref_model.load_state_dict(ck2["model"])
+    opt = torch.optim.Adam(ref_model.parameters(), lr=1.0, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0, amsgrad=True)
+    opt.load_state_dict(ck2["optimizer"])
+    assert abs(opt.param_groups[0]["lr"] - 5e-4) < 1e-12
+    st = opt.state[next(iter(ref_model.parameters()))]
+    assert float(st["step"]) == 4.0 and float(st["max_exp_avg_sq"].abs().max()) > 0
+    tr3 = DataParallelTrainer(ref_model, crit, lr=1.0)
+    tr3.load_state_dict(ck2["optimizer"])
+    assert tr3.step_count == 4 and torch.equal(tr3.exp_avg, trainers[1].exp_avg)
+
+
+def test_train_dropin_runs_the_reference_loop(tmp_path):
+    """sed_b200.train.train: the reference's train() signature on a tiny in-memory loader; writes its checkpoints."""
+    from sed_b200.train import train
+
+    class DS(torch.utils.data.Dataset):
+        def __len__(self):
+            return 32
+
+        def __getitem__(self, i):
+            g = torch.Generator().manual_seed(i)
+            return torch.randn(1, 30, 64, generator=g), (torch.rand(30, 1, generator=g) > 0.8).float()
+
+        def get_validation_sampler(self, max_validate_num=None):
+            for i in range(2):
+                g = torch.Generator().manual_seed(100 + i)
+                yield torch.randn(1, 1, 182, 64, generator=g), (torch.rand(1, 182, 1, generator=g) > 0.8).float(), f"clip{i}"
+
+    loader = torch.utils.data.DataLoader(DS(), batch_size=8, shuffle=False, drop_last=True)
+    m, _ = refmodels.seeded_cnn(refmodels.MAIN_CFG)
+    logs = []
+    trainer, hist = train(m, loader, WeightedBCE(recall_factor=5, multi_frame=True), num_steps=6, lr=1e-4, log_freq=3,
+                          outputs_dir=str(tmp_path), device=torch.device("cuda"), log=logs.append)
+    assert trainer.step_count == 6 and len(hist["train_loss"]) == 6 and all(np.isfinite(hist["train_loss"]))
+    assert len(hist["val"]) == 2 and len(hist["val"][0][1]) == 2            # two evaluations of two clips
+    assert os.path.exists(os.path.join(tmp_path, "checkpoints", "iteration_3.pth"))
+    ck = torch.load(os.path.join(tmp_path, "checkpoints", "iteration_6.pth"), weights_only=False)
+    assert set(ck) == {"iterations", "model", "optimizer"} and ck["iterations"] == 6
+    assert len(logs) == 2 and "lr:" in logs[0]
