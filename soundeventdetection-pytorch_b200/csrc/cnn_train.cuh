@@ -52,14 +52,13 @@ __device__ __forceinline__ void bn_channel_consts(const double* __restrict__ sum
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ z, int n_img, int C, int H, int W, int S,
                                                        double* __restrict__ sums) {
     const int kg = blockIdx.y, nkg = C / 8, Wp = W + 2;
-    const long long total = static_cast<long long>(n_img) * H * W;
+    const int total = n_img * H * W;                 // < 2^31 (checked by the host)
     float s[8], ss[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s[i] = ss[i] = 0.f;
-    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int w = static_cast<int>(idx % W), h = static_cast<int>((idx / W) % H);
-        const long long img = idx / (static_cast<long long>(W) * H);
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int w = idx % W, h = (idx / W) % H;
+        const long long img = idx / (W * H);
         const float4* p = reinterpret_cast<const float4*>(z + ((img * nkg + kg) * S + kConvLead + (h + 1) * Wp + w + 1) * 8);
         const float4 v0 = p[0], v1 = p[1];
         const float v[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -119,13 +118,12 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
     __syncthreads();
     const int nkg = C / 8, Wp = W + 2;
     const int Ho = H / pool, Wo = W / pool, Wpo = Wo + 2;
-    const long long total = static_cast<long long>(n_img) * Ho * Wo * nkg;
-    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int wo = static_cast<int>(idx % Wo);
-        const int ho = static_cast<int>((idx / Wo) % Ho);
-        const int kg = static_cast<int>((idx / (static_cast<long long>(Wo) * Ho)) % nkg);
-        const long long img = idx / (static_cast<long long>(Wo) * Ho * nkg);
+    const int total = n_img * Ho * Wo * nkg;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int wo = idx % Wo;
+        const int ho = (idx / Wo) % Ho;
+        const int kg = (idx / (Wo * Ho)) % nkg;
+        const long long img = idx / (Wo * Ho * nkg);
         const float* zp = z + ((img * nkg + kg) * S_z + kConvLead) * 8;
         float y[8];
 #pragma unroll
@@ -287,11 +285,10 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
     float s1[8], s2[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) s1[i] = s2[i] = 0.f;
-    const long long total = static_cast<long long>(n_img) * H * W;
-    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int w = static_cast<int>(idx % W), h = static_cast<int>((idx / W) % H);
-        const long long img = idx / (static_cast<long long>(W) * H);
+    const int total = n_img * H * W;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int w = idx % W, h = (idx / W) % H;
+        const long long img = idx / (W * H);
         const float4* p = reinterpret_cast<const float4*>(z + ((img * nkg + kg) * S_z + kConvLead + (h + 1) * Wp + w + 1) * 8);
         const float4 v0 = p[0], v1 = p[1];
         const float zz[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
@@ -361,11 +358,10 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
 #pragma unroll
         for (int i = 0; i < 72; ++i) wacc[i] = 0.f;
     }
-    const long long total = static_cast<long long>(n_img) * H * W;
-    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int w = static_cast<int>(idx % W), h = static_cast<int>((idx / W) % H);
-        const long long img = idx / (static_cast<long long>(W) * H);
+    const int total = n_img * H * W;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const int w = idx % W, h = (idx / W) % H;
+        const long long img = idx / (W * H);
         const long long v = kConvLead + (h + 1) * Wp + w + 1;
         const float4* p = reinterpret_cast<const float4*>(z + ((img * nkg + kg) * S_z + v) * 8);
         const float4 v0 = p[0], v1 = p[1];
@@ -434,15 +430,16 @@ struct WgradParams {
     int n_pc;                // pixel chunks (grid.x)
     int Px;                  // X patch pixels per item (Pb + 2, rounded up to 8)
     int stage_bytes;         // one stage: dZ patch + X patch
+    int n_stages;            // 2..4 stages in flight (the loaders run ahead of the MMAs by n_stages - 1 items)
 };
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const WgradParams p) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint64_t bars[6];
+    __shared__ uint64_t bars[10];
     __shared__ uint32_t tmem_ptr_s;
-    uint64_t* full = bars + 0;       // [2] stage loaded (4 loader warps)
-    uint64_t* empty = bars + 2;      // [2] stage consumed (commit)
-    uint64_t* done = bars + 4;       // all MMAs complete
+    uint64_t* full = bars + 0;       // [4] stage loaded (4 loader warps)
+    uint64_t* empty = bars + 4;      // [4] stage consumed (commit)
+    uint64_t* done = bars + 8;       // all MMAs complete
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int pc = blockIdx.x, tg = blockIdx.y;
     const int mt = blockIdx.z / ((p.cin + 127) / 128), nt_ = blockIdx.z % ((p.cin + 127) / 128);
@@ -451,7 +448,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const WgradPa
     const int nkg_o = p.cout / 8, nkg_i = p.cin / 8;
     const int mkg = Mrows / 8, nkg = N / 8;
     if (tid == 0) {
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 4; ++i) {
             mbar_init(&full[i], 4);
             mbar_init(&empty[i], 1);
         }
@@ -471,13 +468,15 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const WgradPa
     const int dh = tg - 1;
 
     if (warp < 4) {
-        // ---------------------------------------------------------------- loaders: planes -> shared memory (16-byte vectors)
+        // ---------------------------------------------------------------- loaders: planes -> shared memory with cp.async
+        // (16 bytes per copy, no register staging: a thread fires every copy of the item and waits once; the
+        // register-staged loop this replaces paid one L2 round trip per plane row, ~14 us per item)
         for (int it = 0; it < n_items; ++it) {
             const int item = pc + it * p.n_pc;
             const int img = item / p.n_bands, band = item % p.n_bands;
             const int v0 = p.Wp + band * p.Pb;                 // first padded pixel of the band (row 1, col 0 = image row 0)
-            const int buf = it & 1;
-            if (it >= 2) mbar_wait(&empty[buf], ((it - 2) >> 1) & 1);
+            const int buf = it % p.n_stages, use = it / p.n_stages;
+            if (use > 0) mbar_wait(&empty[buf], (use - 1) & 1);
             uint8_t* st = smem + buf * p.stage_bytes;
             // dZ patch: pixels [v0, v0 + Pb) of every (half, plane) row; a warp takes whole rows, lanes run along pixels
             for (int row = warp; row < 2 * mkg; row += 4) {
@@ -485,7 +484,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const WgradPa
                 const long long plane = (static_cast<long long>(img) * 2 + half) * nkg_o + (co0 >> 3) + pl;
                 const uint4* src = reinterpret_cast<const uint4*>(p.dz + (plane * p.S_dz + kConvLead + v0) * 16);
                 uint4* dst = reinterpret_cast<uint4*>(st + half * dz_half + pl * p.Pb * 16);
-                for (int px = lane; px < p.Pb; px += 32) dst[px] = src[px];
+                for (int px = lane; px < p.Pb; px += 32) cp_async16(dst + px, src + px);
             }
             // X patch: pixels [v0 + dh Wp - 1, ... + Px)
             const int xs = v0 + dh * p.Wp - 1;
@@ -494,8 +493,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const WgradPa
                 const long long plane = (static_cast<long long>(img) * 2 + half) * nkg_i + (ci0 >> 3) + pl;
                 const uint4* src = reinterpret_cast<const uint4*>(p.x + (plane * p.S_x + kConvLead + xs) * 16);
                 uint4* dst = reinterpret_cast<uint4*>(st + x_off + half * x_half + pl * p.Px * 16);
-                for (int px = lane; px < p.Px; px += 32) dst[px] = src[px];
+                for (int px = lane; px < p.Px; px += 32) cp_async16(dst + px, src + px);
             }
+            cp_async_wait_all();                               // all of this thread's copies have landed
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[buf]);
@@ -524,8 +524,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const WgradPa
         if (tmem != 0) __trap();
         const uint32_t idesc = make_idesc(kFmtBF16, kMajorMN, kMajorMN, 128, N);
         for (int it = 0; it < n_items; ++it) {
-            const int buf = it & 1;
-            mbar_wait(&full[buf], (it >> 1) & 1);
+            const int buf = it % p.n_stages;
+            mbar_wait(&full[buf], (it / p.n_stages) & 1);
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t st = smem_u32(smem + buf * p.stage_bytes);
@@ -562,18 +562,68 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const WgradPa
     }
 }
 
-// dW[co][ci][tap] = sum_pc part[pc][tap][ci][co]  (fixed order: bit-reproducible), written into the flat gradient bucket
-__global__ void __launch_bounds__(256) wgrad_finalize_kernel(const float* __restrict__ part, int n_pc, int cout, int cin,
-                                                             float* __restrict__ d_w) {
-    const long long total = static_cast<long long>(cout) * cin * 9;
-    const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-    if (idx >= total) return;
-    const int co = static_cast<int>(idx % cout);
-    const int ci = static_cast<int>((idx / cout) % cin);
-    const int tap = static_cast<int>(idx / (static_cast<long long>(cout) * cin));
-    float a = 0.f;
-    for (int pc = 0; pc < n_pc; ++pc) a += part[((static_cast<long long>(pc) * 9 + tap) * cin + ci) * cout + co];
-    d_w[(static_cast<long long>(co) * cin + ci) * 9 + tap] = a;
+// dW[co][ci][tap] = sum_pc part[pc][tap][ci][co]  (fixed order: bit-reproducible), written into the gradient buffers.
+// One launch for all tensor-core layers of the model: blockIdx.y = layer.
+constexpr int kTrainMaxLayers = 16;
+struct WgradFinalizeAll {
+    int n;
+    struct {
+        const float* part;
+        float* d_w;
+        int n_pc, cout, cin;
+    } L[kTrainMaxLayers];
+};
+__global__ void __launch_bounds__(256) wgrad_finalize_kernel(const WgradFinalizeAll f) {
+    const auto& L = f.L[blockIdx.y];
+    const long long total = static_cast<long long>(L.cout) * L.cin * 9;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int co = static_cast<int>(idx % L.cout);
+        const int ci = static_cast<int>((idx / L.cout) % L.cin);
+        const int tap = static_cast<int>(idx / (static_cast<long long>(L.cout) * L.cin));
+        float a = 0.f;
+        for (int pc = 0; pc < L.n_pc; ++pc) a += L.part[((static_cast<long long>(pc) * 9 + tap) * L.cin + ci) * L.cout + co];
+        L.d_w[(static_cast<long long>(co) * L.cin + ci) * 9 + tap] = a;
+    }
+}
+
+// bf16 hi|lo packs of every tensor-core layer's current weights in ONE launch (blockIdx.y = layer): the forward
+// convolution and its data-gradient transpose (see pack_conv_weight_kernel for the layout)
+struct PackTrainAll {
+    int n;
+    struct {
+        const float* w;
+        uint8_t* fwd;
+        uint8_t* dgrad;
+        int cout, cin, ct, ck, dct, dck;          // forward: cout tile / cin chunk; data gradient: its cout (= cin) tile / cin (= cout) chunk
+    } L[kTrainMaxLayers];
+};
+__device__ __forceinline__ void pack_store_bf16(uint8_t* out, float v, int co, int ci, int tap, int cout_tile, int cin_chunk,
+                                                int cin) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    const int ntile = co / cout_tile, n = co % cout_tile;
+    const int kc = ci / cin_chunk, cil = ci % cin_chunk;
+    const int ks = cil / 16, k = cil % 16;
+    const int n_kchunks = cin / cin_chunk, ks_chunk = cin_chunk / 16;
+    const long long block = ((static_cast<long long>(ntile) * n_kchunks + kc) * ks_chunk + ks) * 9 + tap;
+    const long long base = block * (cout_tile * 64);
+    const int off = (k / 8) * (cout_tile * 32) + n * 16 + (k % 8) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(out + base + off) = h;
+    *reinterpret_cast<__nv_bfloat16*>(out + base + cout_tile * 16 + off) = l;
+}
+__global__ void __launch_bounds__(256) pack_train_weights_kernel(const PackTrainAll f) {
+    const auto& L = f.L[blockIdx.y];
+    const long long total = static_cast<long long>(L.cout) * L.cin * 9;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int tap = static_cast<int>(idx % 9);
+        const int ci = static_cast<int>((idx / 9) % L.cin);
+        const int co = static_cast<int>(idx / (9LL * L.cin));
+        const float v = L.w[idx];
+        pack_store_bf16(L.fwd, v, co, ci, tap, L.ct, L.ck, L.cin);
+        pack_store_bf16(L.dgrad, v, ci, co, 8 - tap, L.dct, L.dck, L.cout);     // w'[ci][co][8 - tap] = w[co][ci][tap]
+    }
 }
 
 // ---- Adam(amsgrad) with the step count and learning rate in device memory (CUDA-graph friendly) ----------------------

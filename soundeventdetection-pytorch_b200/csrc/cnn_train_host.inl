@@ -13,6 +13,7 @@ struct TrainLayer {               // conv layer l = 0 .. nl (0 = block0.conv1 on
     size_t wg_smem = 0;
     int wg_tiles = 1;
     size_t sums_off = 0;          // doubles: [2C] forward sums, then [2C] backward sums
+    size_t part_off = 0;          // weight-gradient partial sums of this layer
 };
 
 struct TrainPlan {
@@ -38,18 +39,20 @@ void plan_wgrad(TrainLayer& T, long long n_img, int num_sms) {
     for (;; Pb -= 16) {
         const int Px = round_up(Pb + 2, 8);
         const size_t stage = static_cast<size_t>(2) * (mkg * Pb + nkg * Px) * 16;
-        if (2 * stage + static_cast<size_t>(16) * Pb * 16 + 1024 <= 220 * 1024 || Pb <= 16) {
+        const size_t slack = static_cast<size_t>(16) * Pb * 16 + 1024;      // M = 128 rows are read whatever C_out is
+        if (2 * stage + slack <= 220 * 1024 || Pb <= 16) {
             w.Pb = Pb;
             w.Px = Px;
             w.stage_bytes = static_cast<int>(stage);
-            T.wg_smem = 2 * stage + static_cast<size_t>(16) * Pb * 16 + 256;
+            w.n_stages = static_cast<int>(std::max<size_t>(2, std::min<size_t>(4, (220 * 1024 - slack) / stage)));
+            T.wg_smem = w.n_stages * stage + slack;
             break;
         }
     }
     w.n_bands = (pixels + w.Pb - 1) / w.Pb;
     T.wg_tiles = ((T.cout + 127) / 128) * ((T.cin + 127) / 128);
     const long long items = n_img * w.n_bands;
-    long long n_pc = (items + 7) / 8;                                // ~8 items per CTA amortise the accumulator drain
+    long long n_pc = (items + 3) / 4;                                // ~4 items per CTA: latency matters more than the drain
     const long long cap = std::max(1, num_sms / (3 * T.wg_tiles));
     w.n_pc = static_cast<int>(std::max<long long>(1, std::min(n_pc, cap)));
 }
@@ -161,14 +164,18 @@ static int cnn_make_train_plan(const sedb_cnn* m, long long n_clips, long long T
         // gradient planes w.r.t. this layer's activation A_l (fp32, geometry of A)
         const size_t gbytes = static_cast<size_t>(n_clips) * (t.cout / 8) * final_plane_S(0, t.A.H, t.A.W) * 32;
         g_max = std::max(g_max, gbytes);
-        if (l >= 1) part_max = std::max(part_max, static_cast<size_t>(t.wg.n_pc) * 9 * t.cin * t.cout * 4);
     }
     plan.g_off = off;
     plan.g_bytes = (g_max + 127) / 128 * 128;
     off += plan.g_bytes;
     plan.part_off = off;
-    plan.part_bytes = (part_max + 127) / 128 * 128;
-    off += plan.part_bytes;
+    for (int l = 1; l <= nl; ++l) {
+        TrainLayer& t = plan.L[l];
+        t.part_off = off;
+        off += (static_cast<size_t>(t.wg.n_pc) * 9 * t.cin * t.cout * 4 + 127) / 128 * 128;
+    }
+    plan.part_bytes = off - plan.part_off;
+    (void)part_max;
     plan.ws_bytes = off;
     plan.tag = tag | 1ull;
     return 0;
@@ -232,7 +239,9 @@ int sedb_cnn_train_forward(sedb_cnn_t* m, float* const* t, int n_tensors, const 
         return fail("sedb_cnn_train_forward: expected %d tensors, got %d", 10 * m->n_blocks + 2, n_tensors);
     for (int i = 0; i < n_tensors; ++i)
         if (!t[i]) return fail("sedb_cnn_train_forward: tensor %d is null", i);
-    if (n_clips < 1 || T < 1 || n_clips > (1 << 20) || T > (1 << 20)) return fail("sedb_cnn_train_forward: bad shape");
+    if (n_clips < 1 || T < 1 || n_clips > (1 << 20) || T > (1 << 20) ||
+        n_clips * T * SEDB_MEL_BINS * m->channels[0] / 8 >= (1LL << 31))
+        return fail("sedb_cnn_train_forward: bad shape (the training kernels index up to 2^31 (pixel, 8-channel group) units)");
     if (reinterpret_cast<uintptr_t>(workspace_dev) & 127) return fail("workspace must be 128-byte aligned");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const TrainPlan* planp = nullptr;
@@ -246,19 +255,29 @@ int sedb_cnn_train_forward(sedb_cnn_t* m, float* const* t, int n_tensors, const 
     double* stats = reinterpret_cast<double*>(ws);
     const int n_img = static_cast<int>(n_clips);
     const int nl = static_cast<int>(m->layers.size());
-    // bf16 hi|lo packs of the current weights: forward convolution and its data-gradient transpose
-    for (int i = 0; i < nl; ++i) {
-        const UmmaLayer& L = m->layers[i];
-        const int b = (i + 1) / 2, which = (i + 1) % 2;
-        const float* w = t[10 * b + which];
-        const long long total = static_cast<long long>(L.cout) * L.cin * L.ntaps;
-        const int blocks = static_cast<int>((total + 255) / 256);
-        sedb::pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(w, m->train->wpack_fwd[i], L.cout, L.cin, L.ntaps, L.cout_tile,
-                                                             L.cin_chunk, 0, 0, 1);
-        const int dct = L.cin > 128 ? 128 : L.cin, dck = L.cout > 128 ? 128 : L.cout;
-        sedb::pack_conv_weight_kernel<<<blocks, 256, 0, st>>>(w, m->train->wpack_dgrad[i], L.cin, L.cout, L.ntaps, dct, dck,
-                                                             0, 1, 1);
-        g_launches.fetch_add(2);
+    // bf16 hi|lo packs of the current weights: forward convolution and its data-gradient transpose (one launch)
+    if (nl > sedb::kTrainMaxLayers) return fail("too many conv layers for the training step");
+    {
+        sedb::PackTrainAll pk;
+        pk.n = nl;
+        long long max_total = 0;
+        for (int i = 0; i < nl; ++i) {
+            const UmmaLayer& L = m->layers[i];
+            const int b = (i + 1) / 2, which = (i + 1) % 2;
+            pk.L[i].w = t[10 * b + which];
+            pk.L[i].fwd = m->train->wpack_fwd[i];
+            pk.L[i].dgrad = m->train->wpack_dgrad[i];
+            pk.L[i].cout = L.cout;
+            pk.L[i].cin = L.cin;
+            pk.L[i].ct = L.cout_tile;
+            pk.L[i].ck = L.cin_chunk;
+            pk.L[i].dct = L.cin > 128 ? 128 : L.cin;
+            pk.L[i].dck = L.cout > 128 ? 128 : L.cout;
+            max_total = std::max(max_total, static_cast<long long>(L.cout) * L.cin * L.ntaps);
+        }
+        dim3 pgrid(static_cast<unsigned>(std::min<long long>((max_total + 255) / 256, 148)), nl);
+        sedb::pack_train_weights_kernel<<<pgrid, 256, 0, st>>>(pk);
+        g_launches.fetch_add(1);
     }
     CUDA_TRY(cudaGetLastError());
     for (int l = 0; l <= nl; ++l) {
@@ -326,7 +345,8 @@ int sedb_cnn_train_backward(sedb_cnn_t* m, float* const* t, int n_tensors, const
         return fail("sedb_cnn_train_backward: the workspace does not hold the forward pass of this shape");
     double* stats = reinterpret_cast<double*>(ws);
     float* G = reinterpret_cast<float*>(ws + plan.g_off);
-    float* part = reinterpret_cast<float*>(ws + plan.part_off);
+    sedb::WgradFinalizeAll fin;
+    fin.n = static_cast<int>(m->layers.size());
     const int n_img = static_cast<int>(n_clips);
     const int nl = static_cast<int>(m->layers.size());
     const int nb = m->n_blocks;
@@ -369,6 +389,7 @@ int sedb_cnn_train_backward(sedb_cnn_t* m, float* const* t, int n_tensors, const
             CUDA_TRY(cudaGetLastError());
             break;
         }
+        if (l > sedb::kTrainMaxLayers) return fail("too many conv layers for the training step");
         sedb::bn_bwd_apply_kernel<0><<<agrid, 256, 0, st>>>(Z, G, stats + tl.sums_off, stats + tl.sums_off + 2 * tl.cout, gamma,
                                                            beta, n_img, tl.cout, tl.H, tl.W, tl.Z.S, tl.pool, S_g, tl.dZ.S,
                                                            ws + tl.dZ.offset, d_gamma, d_beta, nullptr, nullptr);
@@ -377,20 +398,31 @@ int sedb_cnn_train_backward(sedb_cnn_t* m, float* const* t, int n_tensors, const
         sedb::WgradParams wp = tl.wg;
         wp.dz = ws + tl.dZ.offset;
         wp.x = ws + plan.L[l - 1].A.offset;
-        wp.part = part;
+        wp.part = reinterpret_cast<float*>(ws + tl.part_off);
         wp.S_dz = tl.dZ.S;
         wp.S_x = plan.L[l - 1].A.S;
         dim3 wgrid(wp.n_pc, 3, tl.wg_tiles);
         sedb::wgrad_umma_kernel<<<wgrid, sedb::kWgThreads, tl.wg_smem, st>>>(wp);
-        const long long wtotal = static_cast<long long>(tl.cout) * tl.cin * 9;
-        sedb::wgrad_finalize_kernel<<<static_cast<int>((wtotal + 255) / 256), 256, 0, st>>>(part, wp.n_pc, tl.cout, tl.cin, d_w);
-        g_launches.fetch_add(2);
+        fin.L[l - 1].part = wp.part;
+        fin.L[l - 1].d_w = d_w;
+        fin.L[l - 1].n_pc = wp.n_pc;
+        fin.L[l - 1].cout = tl.cout;
+        fin.L[l - 1].cin = tl.cin;
+        g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
         // data gradient: G = dL/dA_{l-1}
         if (int rc = launch_umma_layer<1>(m->ctx, m->train->wpack_dgrad[l - 1], 1, 0, nullptr, nullptr, tl.dgrad,
                                           ws + tl.dZ.offset, reinterpret_cast<uint8_t*>(G), n_img, tl.dZ.S,
                                           final_plane_S(0, tl.H, tl.W), st))
             return rc;
+    }
+    if (nl > 0) {                                                    // all weight gradients: partial sums -> gradient buffers
+        long long max_total = 0;
+        for (int i = 0; i < nl; ++i) max_total = std::max(max_total, static_cast<long long>(fin.L[i].cout) * fin.L[i].cin * 9);
+        dim3 fgrid(static_cast<unsigned>(std::min<long long>((max_total + 255) / 256, 148)), nl);
+        sedb::wgrad_finalize_kernel<<<fgrid, 256, 0, st>>>(fin);
+        g_launches.fetch_add(1);
+        CUDA_TRY(cudaGetLastError());
     }
     return 0;
 }
