@@ -8,7 +8,9 @@ native and multi-GPU:
   statistics, WeightedBCE, backward (``sedb_cnn_train_forward`` / ``sedb_bce_with_logits`` / ``sedb_cnn_train_backward``),
   ONE NCCL all-reduce of the flat gradient bucket (2.33 MB for the main.py model), and the fused Adam-amsgrad update with
   the 1/world_size of the gradient mean folded in.  With ``graph=True`` the iteration -- all-reduce included -- is captured
-  once into a CUDA graph and replayed; the step count and learning rate live in device memory for that.
+  once into a CUDA graph and replayed; the step count and learning rate live in device memory for that.  (NCCL wants
+  the operations of one communicator serialised: after graph-replayed steps, synchronise the stream before issuing an
+  eager collective on the same process group.)
 * parameters and gradients live in ONE flat float32 buffer each (the module's tensors are views);
 * replicas start identical: rank 0's parameters and BatchNorm buffers are broadcast at construction (the reference's
   main.py does not seed model construction); BatchNorm statistics then stay per replica, as in the reference (no SyncBN);
@@ -216,6 +218,11 @@ class DataParallelTrainer:
             self._iteration(sx, st)
         # the capture pass did not execute anything: state is still the restored one
         return g, sx, st
+
+    def close(self):
+        """Drop the captured graphs.  Call before ``dist.destroy_process_group()``: a live CUDA graph that holds NCCL
+        kernels keeps the communicator busy and the teardown waits for it forever."""
+        self._graphs.clear()
 
     # ------------------------------------------------------------------ optimizer
     def _apply_update_dev(self):
