@@ -44,15 +44,37 @@ LOGMEL_MMA_FLOP_PER_FRAME = 96 * 128 * 128 * 16 * 2
 METRIC = "audio-hours/sec (log-mel + CNN frame SED)"
 
 
-def profiled_traffic(clips):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (same clip count)."""
-    try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r1_logmel_full.json")))
-        if int(d.get("clips", -1)) == int(clips):
-            return float(d["traffic_bytes_per_launch"])
-    except Exception:
-        pass
-    return None
+LOGMEL_SOURCES = ("logmel.cuh", "umma.cuh", "host_tables.h")
+
+
+def kernel_source_sha(names=LOGMEL_SOURCES):
+    """sha256 over the sources of a kernel: ties a committed ncu capture to the code it was taken from."""
+    import hashlib
+    h = hashlib.sha256()
+    for n in names:
+        with open(os.path.join(ROOT, "soundeventdetection-pytorch_b200", "csrc", n), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def profiled_logmel(clips):
+    """DRAM bytes per launch and tensor-pipe activity of the dominant kernel from the newest committed `ncu --set full`
+    capture (profiles/r*_logmel_full.json, same clip count), and whether the kernel sources changed since it was taken."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_logmel_full.json"))):
+        try:
+            d = json.load(open(path))
+            if int(d.get("clips", -1)) == int(clips):
+                best = (path, d)
+        except Exception:
+            pass
+    if best is None:
+        return None
+    path, d = best
+    stale = d.get("source_sha") != kernel_source_sha()
+    return {"traffic": float(d["traffic_bytes_per_launch"]), "pipe_active_pct": float(d["tensor_pipe_active_pct"]),
+            "stale": bool(stale), "capture": os.path.relpath(path, ROOT)}
 
 
 def measured_peaks():
@@ -64,6 +86,13 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, 1400.0, "fallback"
+
+
+def burst_tflops():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+    except Exception:
+        return 1600.0
 
 
 class ClockSampler:
@@ -201,6 +230,52 @@ def run_reference(args):
             "gpu_launches": 0}
     emit(line)
 
+
+
+# ------------------------------------------------------------------------------------------------- host <-> device path
+def bind_to_gpu_numa(index):
+    """Pin this process to the CPUs of the GPU's NUMA node BEFORE any pinned allocation, so that the staging memory of
+    the end-to-end path is node-local (first touch).  Returns a short description (or why it was skipped)."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(index)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = f"/sys/bus/pci/devices/{bdf}"
+        node = int(open(f"{base}/numa_node").read().strip())
+        cpus = set()
+        for part in open(f"{base}/local_cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if node < 0 or not cpus:
+            return f"{bdf}: no NUMA information"
+        os.sched_setaffinity(0, cpus)
+        return f"{bdf}: NUMA node {node}, {len(cpus)} CPUs"
+    except Exception as e:                                               # noqa: BLE001
+        return f"skipped ({type(e).__name__})"
+
+
+def h2d_ceiling(host, dev, chunk_bytes=64 << 20, reps=3):
+    """Pure pinned host -> device copy rate (GB/s, this rank) with the chunking of the end-to-end pipeline and every
+    rank copying at the same time: the ceiling the host-buffer `e2e` figure can reach on this box."""
+    import torch
+    from sed_b200 import parallel
+    flat = host.view(torch.uint8).reshape(-1)
+    stage = [torch.empty(chunk_bytes, dtype=torch.uint8, device=dev) for _ in range(2)]
+    st = torch.cuda.Stream(device=dev)
+    best = 0.0
+    for _ in range(reps):
+        torch.cuda.synchronize()
+        parallel.barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(st):
+            for i, off in enumerate(range(0, flat.numel(), chunk_bytes)):
+                n = min(chunk_bytes, flat.numel() - off)
+                stage[i & 1][:n].copy_(flat[off:off + n], non_blocking=True)
+        st.synchronize()
+        dt = parallel.max_over_ranks(time.perf_counter() - t0, dev)
+        best = max(best, flat.numel() / dt / 1e9)
+    return best
 
 
 # ------------------------------------------------------------------------------------------------- other BASELINE configs
@@ -374,6 +449,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device (the hot path has no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa(local_rank) if not args.no_numa_bind else "disabled"
     lib = _ext.load()
     C = args.clips
 
@@ -451,6 +527,8 @@ def run_ours(args):
     e2e_ms = parallel.max_over_ranks((time.perf_counter() - w0) * 1e3 / e2e_steps, dev)
     e2e_ok = bool(torch.allclose(host_probs, probs[:Ce].cpu(), atol=1e-4))
     e2e_value = world * Ce * CLIP_SECONDS / 3600.0 / (e2e_ms * 1e-3)
+    h2d_gbs = h2d_ceiling(host_wave, dev)                      # per rank, all ranks copying concurrently
+    e2e_gbs = Ce * CLIP_SAMPLES * 4 / (e2e_ms * 1e-3) / 1e9
 
     # ---- the same clips as 16-bit PCM (the WAV data chunk): not the headline configuration, reported
     # beside it because it halves the bytes per clip in HBM and over PCIe
@@ -503,6 +581,8 @@ def run_ours(args):
 
     if rank != 0:
         return
+    prof = profiled_logmel(C)
+    burst = burst_tflops()
     achieved = C * ALGO_BYTES_PER_CLIP / (lm_ms * 1e-3) / 1e9
     tflops = C * FRAMES * LOGMEL_MMA_FLOP_PER_FRAME / (lm_ms * 1e-3) / 1e12
     line = {
@@ -515,14 +595,24 @@ def run_ours(args):
                    "clips_per_gpu": C, "l2_policy": "inputs (2.95 GB/GPU) larger than L2",
                    "stage_ms": {"logmel": lm_ms, "cnn": cnn_ms}},
         "roofline": {"kernel": "logmel_fused_kernel", "bound": "hbm", "achieved": achieved, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": profiled_traffic(C), "peak_source": src,
-                     "algorithmic_bytes_per_launch": C * ALGO_BYTES_PER_CLIP, "ms_per_launch": lm_ms},
-        "tensor": {"kernel": "logmel_fused_kernel", "executed_tflops": tflops, "peak": tf_peak, "unit": "TFLOP/s",
-                   "frac": tflops / tf_peak, "note": "split-operand DFT GEMMs executed on tcgen05; the MMAs run at their hardware floor (about a third of the frame time), the rest is operand production and the exposed frame load"},
+                     "unit": "GB/s", "frac": achieved / hbm_peak, "traffic": prof["traffic"] if prof else None,
+                     "traffic_stale": prof["stale"] if prof else None, "traffic_capture": prof["capture"] if prof else None,
+                     "peak_source": src, "algorithmic_bytes_per_launch": C * ALGO_BYTES_PER_CLIP, "ms_per_launch": lm_ms},
+        "tensor": {"kernel": "logmel_fused_kernel", "unit": "TFLOP/s", "peak_burst": burst,
+                   "useful_tflops": tflops / 3.0, "frac_useful_of_burst_peak": tflops / 3.0 / burst,
+                   "executed_tflops": tflops, "frac_executed_of_burst_peak": tflops / burst,
+                   "pipe_active_pct_ncu": prof["pipe_active_pct"] if prof else None,
+                   "pipe_active_stale": prof["stale"] if prof else None,
+                   "note": "useful = the factored DFT's GEMM FLOPs once (16.8 MFLOP/frame, both stages); executed = "
+                           "x3 for the hi/lo split products; pipe_active = sm__pipe_tensor_cycles_active from the committed "
+                           "ncu capture (stale = kernel sources changed since)"},
         "cnn": {"ms": cnn_ms, "algorithmic_tflops": C * CNN_FLOP_PER_CLIP / (cnn_ms * 1e-3) / 1e12},
         "e2e": {"value": e2e_value, "unit": "audio-hours/sec", "h2d_bytes_per_step": Ce * CLIP_SAMPLES * 4 + 512,
                 "d2h_bytes_per_step": Ce * 176 * 4, "ms_per_step": e2e_ms, "clips_per_step": Ce,
-                "matches_device_path": e2e_ok},
+                "matches_device_path": e2e_ok, "h2d_gbs_per_gpu": e2e_gbs, "h2d_ceiling_gbs_per_gpu": h2d_gbs,
+                "frac_of_h2d_ceiling": e2e_gbs / h2d_gbs if h2d_gbs else None, "numa_binding": numa,
+                "note": "h2d_ceiling = pure pinned host->device copies of the same buffer in the same 64 MB chunks with "
+                        "every rank copying at once; the end-to-end path cannot beat it on this box"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -564,6 +654,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pcm16", action="store_true", help="skip the 16-bit PCM variant of the measurement")
+    ap.add_argument("--no-numa-bind", action="store_true", help="do not pin the process to the GPU's NUMA node")
     ap.add_argument("--no-configs", action="store_true", help="skip the config3 / config4 / config5 sub-measurements")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -702,9 +702,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
 
             SEDB_PROF(1);   // fold / split / store
             // ---------------------------------------------------------------- twiddle, radix-2, stage-2 A operand
-            mbar_wait(d1_full, it & 1);
-            tc_fence_after();
-            SEDB_PROF(2);   // wait for stage-1 MMAs
+            // (the row-128 input Y[n2,128] only needs the fold's partial sums: formed while the last stage-1 MMAs drain)
             worker_sync();                                            // x128_s / alt_s visible to all workers
             if (tid < 128) {
                 float acc = x128_s[tid];
@@ -712,6 +710,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 for (int rr = 0; rr < 16; ++rr) acc += alt_s[rr * 128 + tid];
                 v_s[tid] = acc;                                       // Y[n2,128] (scaled)
             }
+            mbar_wait(d1_full, it & 1);
+            tc_fence_after();
+            SEDB_PROF(2);   // wait for stage-1 MMAs
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 // chunk c = columns n in [16 c, 16 c + 16) (and n + 64); this thread owns n = na + {0, 1, 8, 9}.

@@ -70,8 +70,11 @@ def logmel(rep, tag, command):
     d = raw(rep)[0]
     clips = 256
     rd, wr = num(d, "dram__bytes_read.sum"), num(d, "dram__bytes_write.sum")
+    sys.path.insert(0, ROOT)
+    import bench
     out = {
         "command": command, "kernel": "sedb::logmel_fused_kernel<0>", "clips": clips,
+        "source_sha": bench.kernel_source_sha(),
         "gpu_time_ms": num(d, "gpu__time_duration.sum"),
         "dram_bytes_read": rd, "dram_bytes_write": wr, "traffic_bytes_per_launch": rd + wr,
         "algorithmic_bytes_per_launch": clips * 11566592,
