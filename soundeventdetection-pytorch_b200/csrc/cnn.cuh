@@ -190,7 +190,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
         band = item % p.n_bands;
         img = item / p.n_bands;
     };
-    auto band_v0 = [&](int band) { return p.mode == 0 ? (p.R * band + 1) * p.Wp : 1 + band * 128 * p.n_tiles; };
+    // first pixel of a band: 2-D bands start at the first REAL pixel of their first row (column 1 of the padded row), so
+    // that band pixel pp sits in column pp % Wp of the image and 2x2 pooling pairs are (even, odd) lane pairs
+    auto band_v0 = [&](int band) { return p.mode == 0 ? (p.R * band + 1) * p.Wp + 1 : 1 + band * 128 * p.n_tiles; };
 
     if (warp >= 9) {
         // ================================================================ bulk-copy producers (converged warps, one
@@ -380,10 +382,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                 for (int m = grp; m < p.n_tiles; m += 2) {
                     const int pp = 128 * m + 32 * q + lane;
                     bool valid = pp < npix;
-                    if (p.mode == 0) {
-                        const int col = pp % p.Wp;
-                        valid = valid && col >= 1 && col <= p.W;
-                    }
+                    if (p.mode == 0) valid = valid && (pp % p.Wp) < p.W;
                     const long long vout = kConvLead + v0 + pp;
                     for (int c0 = 0; c0 < p.cout_sub; c0 += 16) {
                         float acc[16];
@@ -411,65 +410,73 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
                     }
                 }
             } else {
-                // pooled: stage `cstep` channels of every band pixel, then reduce windows
-                const int cstep = p.cstep, sstr = cstep + 1;
-                for (int c0 = 0; c0 < p.cout_sub; c0 += cstep) {
-                    for (int m = grp; m < p.n_tiles; m += 2) {
-                        const int pp = 128 * m + 32 * q + lane;
-                        for (int c1 = 0; c1 < cstep; c1 += 16) {
-                            float acc[16];
-                            load16(m, c0 + c1, acc);
+                if (p.mode == 0) {
+                    // 2x2 average pooling.  Horizontal pairs are (even, odd) lanes: one shuffle; the pair sums of `cstep`
+                    // channels go to shared memory (row-major over pair index pp / 2), and the vertical partner of pair
+                    // j is pair j + Wp / 2.
+                    const int cstep = p.cstep, sstr = cstep + 1;
+                    for (int c0 = 0; c0 < p.cout_sub; c0 += cstep) {
+                        for (int m = grp; m < p.n_tiles; m += 2) {
+                            const int pp = 128 * m + 32 * q + lane;
+                            float* st = stage + (pp >> 1) * sstr;
+                            for (int c1 = 0; c1 < cstep; c1 += 16) {
+                                float acc[16];
+                                load16(m, c0 + c1, acc);
 #pragma unroll
-                            for (int i = 0; i < 16; ++i)
-                                stage[pp * sstr + c1 + i] =
-                                    fmaxf(0.f, fmaf(acc[i], sc_s[n0 + c0 + c1 + i], sh_s[n0 + c0 + c1 + i]));
+                                for (int i = 0; i < 16; ++i) {
+                                    const float y = fmaxf(0.f, fmaf(acc[i], sc_s[n0 + c0 + c1 + i], sh_s[n0 + c0 + c1 + i]));
+                                    acc[i] = y + __shfl_xor_sync(0xffffffffu, y, 1);
+                                }
+                                if ((lane & 1) == 0) {
+#pragma unroll
+                                    for (int i = 0; i < 16; ++i) st[c1 + i] = acc[i];
+                                }
+                            }
                         }
-                    }
-                    epi_sync();
-                    const int ngrp = cstep / 8;                      // 8-channel groups per pass
-                    if (p.mode == 0) {
-                        // avg 2x2: work unit = (pooled pixel, 8-channel group)
-                        const int npool = (p.R / 2) * p.Wo;
+                        epi_sync();
+                        const int ngrp = cstep / 8;                      // 8-channel groups per pass
+                        const int npool = (p.R / 2) * p.Wo, half_wp = p.Wp >> 1;
                         for (int u = etid; u < npool * ngrp; u += 256) {
-                            const int half = u % ngrp, pix = u / ngrp;
+                            const int g8 = u % ngrp, pix = u / ngrp;
                             const int r2 = pix / p.Wo, w2 = pix % p.Wo;
                             const int ho = (p.R / 2) * band + r2;
                             if (r2 < rows_eff / 2 && ho < p.Ho) {
-                                const int base = (2 * r2) * p.Wp + 2 * w2 + 1;
+                                const float* a = stage + (r2 * p.Wp + w2) * sstr + g8 * 8;
+                                const float* b = a + half_wp * sstr;
                                 float y[8];
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const int c = half * 8 + i;
-                                    y[i] = 0.25f * (stage[base * sstr + c] + stage[(base + 1) * sstr + c] +
-                                                    stage[(base + p.Wp) * sstr + c] + stage[(base + p.Wp + 1) * sstr + c]);
-                                }
+                                for (int i = 0; i < 8; ++i) y[i] = 0.25f * (a[i] + b[i]);
                                 const long long vout = kConvLead + (ho + 1) * p.Wpo + w2 + 1;
-                                const long long kg = (n0 + c0) / 8 + half;
+                                const long long kg = (n0 + c0) / 8 + g8;
                                 store_h8(p.out + ((out_img + kg) * p.S_out + vout) * 16, y);
                             }
                         }
-                    } else {
-                        // max over 4 consecutive positions: work unit = (pooled position, 8-channel group)
-                        const int npool = 32 * p.n_tiles;
-                        for (int u = etid; u < npool * ngrp; u += 256) {
-                            const int half = u % ngrp, pos2 = u / ngrp;
-                            const int po = band * 32 * p.n_tiles + pos2;
-                            if (po < p.Wo) {
-                                float y[8];
+                        epi_sync();
+                    }
+                } else {
+                    // max over 4 consecutive positions (1-D): lanes 4j .. 4j + 3, two shuffles, no shared memory
+                    for (int m = grp; m < p.n_tiles; m += 2) {
+                        const int pp = 128 * m + 32 * q + lane;
+                        const int po = band * 32 * p.n_tiles + (pp >> 2);
+                        for (int c0 = 0; c0 < p.cout_sub; c0 += 16) {
+                            float acc[16];
+                            load16(m, c0, acc);
 #pragma unroll
-                                for (int i = 0; i < 8; ++i) {
-                                    const int c = half * 8 + i;
-                                    const int b0 = 4 * pos2;
-                                    y[i] = fmaxf(fmaxf(stage[b0 * sstr + c], stage[(b0 + 1) * sstr + c]),
-                                                 fmaxf(stage[(b0 + 2) * sstr + c], stage[(b0 + 3) * sstr + c]));
-                                }
+                            for (int i = 0; i < 16; ++i) {
+                                float y = fmaxf(0.f, fmaf(acc[i], sc_s[n0 + c0 + i], sh_s[n0 + c0 + i]));
+                                y = fmaxf(y, __shfl_xor_sync(0xffffffffu, y, 1));
+                                acc[i] = fmaxf(y, __shfl_xor_sync(0xffffffffu, y, 2));
+                            }
+                            if ((lane & 3) == 0 && po < p.Wo) {
                                 const long long vout = kConvLead + 1 + po;
-                                const long long kg = (n0 + c0) / 8 + half;
-                                store_h8(p.out + ((out_img + kg) * p.S_out + vout) * 16, y);
+#pragma unroll
+                                for (int g2 = 0; g2 < 2; ++g2) {
+                                    const long long kg = (n0 + c0) / 8 + g2;
+                                    store_h8(p.out + ((out_img + kg) * p.S_out + vout) * 16, acc + 8 * g2);
+                                }
                             }
                         }
                     }
-                    epi_sync();
                 }
             }
             tc_fence_before();

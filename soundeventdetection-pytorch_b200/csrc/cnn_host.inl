@@ -38,9 +38,11 @@ size_t conv_smem_bytes(const sedb::ConvParams& p) {
 // trips for the MMA issuer), then as many slots as fit.
 bool conv_fit_smem(sedb::ConvParams& p) {
     const int wblock = p.cout_tile * 64;
-    for (int cstep = (p.pool != 1 && p.cout_sub % 32 == 0) ? 32 : 16; cstep >= 16; cstep -= 16) {
+    const bool staged = (p.pool == 2 && p.mode == 0);             // 2x2 pooling exchanges pair sums through shared memory
+    for (int cstep = 64; cstep >= 16; cstep /= 2) {
+        if (staged && p.cout_sub % cstep) continue;
         p.cstep = cstep;
-        p.stage_bytes = (p.pool != 1) ? 128 * p.n_tiles * (cstep + 1) * 4 : 0;
+        p.stage_bytes = staged ? 64 * p.n_tiles * (cstep + 1) * 4 : 0;
         for (int kpb = p.ntaps; kpb >= 1; --kpb) {                 // taps per slot: all of them, 3 or 1 (conv_issue.cuh)
             if (p.ntaps % kpb || (kpb != p.ntaps && kpb != 3 && kpb != 1) || kpb * wblock > sedb::kConvMaxWSlotBytes)
                 continue;
@@ -51,9 +53,10 @@ bool conv_fit_smem(sedb::ConvParams& p) {
                 if (conv_smem_bytes(p) <= 227 * 1024) return true;
             }
         }
+        if (!staged) break;
     }
     p.cstep = 16;
-    p.stage_bytes = (p.pool != 1) ? 128 * p.n_tiles * 17 * 4 : 0;
+    p.stage_bytes = staged ? 64 * p.n_tiles * 17 * 4 : 0;
     p.kpb = 1;
     p.wslot_bytes = wblock;
     p.n_wslots = 2;
@@ -118,7 +121,7 @@ bool plan_candidate(const UmmaLayer& L, int H, int W, int amode, int max_tiles, 
     p.P = 128 * p.n_tiles + 2 * p.halo;
     p.patch_bytes = (1 + amode) * (L.cin_chunk / 8) * p.P * 16;
     if (!conv_fit_smem(p)) return false;
-    const int v0_last = (L.mode == 0) ? (p.R * (p.n_bands - 1) + 1) * p.Wp : 1 + (p.n_bands - 1) * 128 * p.n_tiles;
+    const int v0_last = (L.mode == 0) ? (p.R * (p.n_bands - 1) + 1) * p.Wp + 1 : 1 + (p.n_bands - 1) * 128 * p.n_tiles;
     S_in = round_up(sedb::kConvLead + v0_last - p.halo + p.P, 8);
     return true;
 }
