@@ -1,19 +1,20 @@
-"""Small end-to-end pass for compute-sanitizer (memcheck / racecheck / synccheck)."""
+"""compute-sanitizer target: small invocations of every kernel family (log-mel, CNN inference, M5, training step)."""
 import os, sys
-import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-import sed_b200
+import numpy as np, torch
+import sed_b200, refmodels, signals
 from sed_b200.dataset.spectogram import preprocess as P
-import refmodels, signals
-ys = np.stack([signals.hdr(100000, i) for i in range(3)])
-x = P.waveform_to_log_mel(torch.from_numpy(ys).float().cuda())
-pcm = torch.from_numpy(np.clip(np.round(ys[:, :, None].repeat(2, axis=2) * 20000), -32768, 32767).astype(np.int16))
-x16 = P.pcm16_to_log_mel(pcm.cuda())                                   # 2-channel PCM, vector path
-x16b = P.pcm16_to_log_mel(pcm[:, :, :1].repeat(1, 1, 3).contiguous().cuda())   # 3 channels, scalar path
+from sed_b200.train import DataParallelTrainer
+from sed_b200.utils.common import WeightedBCE
+y = np.stack([signals.hdr(100000, i) for i in range(2)])
+lm = P.waveform_to_log_mel(torch.from_numpy(y).float().cuda())
 m, _ = refmodels.seeded_cnn(refmodels.MAIN_CFG); m = m.cuda()
-p = m.logits(torch.randn(2, 1, 37, 64, device="cuda"))
-w, _ = refmodels.seeded_m5(); w = w.cuda()
-q = w(refmodels.m5_inputs(2).cuda())
+p = m.logits(torch.randn(3, 1, 61, 64, device="cuda"))
+m5, _ = refmodels.seeded_m5(); m5 = m5.cuda()
+q = m5(torch.randn(2, 1, 31680, device="cuda") * 0.1)
+tr = DataParallelTrainer(m, WeightedBCE(recall_factor=5, multi_frame=True), lr=1e-4)
+for _ in range(2):
+    loss = tr.step(torch.randn(5, 1, 30, 64, device="cuda"), (torch.rand(5, 30, 1, device="cuda") > 0.8).float())
 torch.cuda.synchronize()
-print("ok", x.shape, x16.shape, x16b.shape, p.shape, q.shape)
+print("ok", lm.shape, p.shape, q.shape, float(loss))
