@@ -70,3 +70,35 @@ def test_two_rank_single_bucket_gradient_allreduce():
     assert n0 == n1 == 8 * 4 + 4 + 4 + 1
     assert torch.allclose(s0, l0 + l1) and torch.equal(s0, s1)
     assert not torch.equal(l0, l1)
+
+
+def _bcast_worker(rank, world, port, ret):
+    sys.path.insert(0, ROOT)
+    import sed_b200  # noqa: F401
+    from sed_b200 import parallel
+    from sed_b200.models.spectogram_models import Cnn_AvgPooling
+    from sed_b200.train import FlatBuffers, broadcast_module_
+    os.environ.update(RANK=str(rank), LOCAL_RANK=str(rank), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1",
+                      MASTER_PORT=str(port))
+    parallel.init_process_group("gloo")
+    torch.manual_seed(100 + rank)                          # the reference's main.py does not seed model construction
+    net = Cnn_AvgPooling(1, model_config=[(16, 2), (16, 1)])
+    with torch.no_grad():
+        net.conv_blocks[0].bn1.running_mean.fill_(float(rank))
+    flat = FlatBuffers(net)
+    before = flat.param.clone()
+    broadcast_module_(net, flat.param)                     # what DataParallelTrainer does at construction
+    ret[rank] = (before, flat.param.clone(), net.conv_blocks[0].bn1.running_mean.clone(),
+                 net.event_fc.weight.data_ptr() == flat.param[-17:-1].data_ptr())
+    dist.destroy_process_group()
+
+
+def test_two_rank_replicas_start_from_rank0_parameters_and_buffers():
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_bcast_worker, args=(2, 29651, ret), nprocs=2, join=True)
+    (b0, a0, rm0, v0), (b1, a1, rm1, v1) = ret[0], ret[1]
+    assert not torch.equal(b0, b1)                         # different initial weights ...
+    assert torch.equal(a0, b0) and torch.equal(a1, b0)     # ... every rank ends up with rank 0's
+    assert torch.equal(rm0, rm1) and float(rm1[0]) == 0.0  # buffers too
+    assert v0 and v1                                       # the module's tensors are views of the flat buffer
