@@ -25,11 +25,28 @@
 // per-frame power-of-two block scale so that the fp16 range is never exceeded).
 #pragma once
 #include "umma.cuh"
+#include <type_traits>
 
 // cp.async.bulk.prefetch.L2 of the next frame by the copy warp (0 disables it for A/B measurements: the frame-load
 // phase is 4.2 k cycles with it, 5.8 k without)
 #ifndef SEDB_L2_PREFETCH
 #define SEDB_L2_PREFETCH 1
+#endif
+// development switches of the worker loop (see the comments at their uses)
+#ifndef SEDB_CONSUMER_FENCE
+#define SEDB_CONSUMER_FENCE 1
+#endif
+#ifndef SEDB_TAIL_FENCE
+#define SEDB_TAIL_FENCE 0
+#endif
+#ifndef SEDB_TW_UNROLL
+#define SEDB_TW_UNROLL 2
+#endif
+#ifndef SEDB_KAHEAD
+#define SEDB_KAHEAD 2
+#endif
+#ifndef SEDB_HROW_PIPE
+#define SEDB_HROW_PIPE 0
 #endif
 
 namespace sedb {
@@ -72,8 +89,9 @@ constexpr int kOffMelTab = kOffCs + 2048;                  // segment table (320
 constexpr int kOffMelPart = kOffMelTab + kMelTabEntries * 16;   // partial moments (2 x kMelMaxPieces floats)
 constexpr int kOffMelCoef = kOffMelPart + 2 * kMelMaxPieces * 4;   // 64 x float4 line coefficients
 constexpr int kOffNorm = kOffMelCoef + 1024;               // mean[64], std[64] (when given)
-constexpr int kOffRed = kOffNorm + 512;                    // absmax reduction scratch (16 floats) + scale
-constexpr int kOffHannRow = kOffRed + 128;                 // window factors per row m: {sin, cos}(pi (128 m - 544)/31679), 257 x float2
+constexpr int kOffRed = kOffNorm + 512;                    // [0,16) abs-max scratch (second half), [20] frame scale for the helpers,
+                                                           // [24] redo flag, [32,48) abs-max scratch (first half)
+constexpr int kOffHannRow = kOffRed + 192;                 // window factors per row m: {sin, cos}(pi (128 m - 544)/31679), 257 x float2
 constexpr int kOffHannLane = kOffHannRow + 2064;           // window factors per column n2: cos[128] then sin[128] of pi n2/31679
 constexpr int kOffE1Tw = kOffHannLane + 1024;              // exp(-2 pi i n/128), n < 64: re[64] then im[64]
 constexpr int kOffBars = kOffE1Tw + 512;                   // mbarriers
@@ -158,19 +176,27 @@ __device__ __forceinline__ void mel_partials(const float* __restrict__ p_s, cons
         const int slot = e.y >> 16;
         const float* p = p_s + k0;
         // straight-line over the maximum piece length (bins past the piece are read and discarded: they are still inside
-        // the spectrum's buffer), so that all loads are in flight before the first add waits; two accumulator pairs;
-        // sum (k - kb) P = (k0 - kb) sum P + sum j P with compile-time j
+        // the spectrum's buffer) in two batches, so that the loads of a batch are in flight before its first add waits
+        // without holding 43 registers; two accumulator pairs; sum (k - kb) P = (k0 - kb) sum P + sum j P with compile-time j
         const float kf0 = static_cast<float>(k0 - (e.y & 0xffff));
         float a0 = 0.f, a1 = 0.f, b0 = 0.f, b1 = 0.f;
+        constexpr int kHalf = (kMelPieceLen + 1) / 2;
 #pragma unroll
-        for (int j = 0; j < kMelPieceLen; j += 2) {
-            const float v0 = (j < len) ? p[j] : 0.f;
-            a0 += v0;
-            b0 = fmaf(static_cast<float>(j), v0, b0);
-            if (j + 1 < kMelPieceLen) {
-                const float v1 = (j + 1 < len) ? p[j + 1] : 0.f;
-                a1 += v1;
-                b1 = fmaf(static_cast<float>(j + 1), v1, b1);
+        for (int h = 0; h < kMelPieceLen; h += kHalf) {
+            float v[kHalf];
+#pragma unroll
+            for (int j = 0; j < kHalf; ++j) v[j] = (h + j < kMelPieceLen && h + j < len) ? p[h + j] : 0.f;
+#pragma unroll
+            for (int j = 0; j < kHalf; ++j) {
+                if (h + j < kMelPieceLen) {
+                    if ((j & 1) == 0) {
+                        a0 += v[j];
+                        b0 = fmaf(static_cast<float>(h + j), v[j], b0);
+                    } else {
+                        a1 += v[j];
+                        b1 = fmaf(static_cast<float>(h + j), v[j], b1);
+                    }
+                }
             }
         }
         const float s0 = a0 + a1;
@@ -220,8 +246,28 @@ __device__ __forceinline__ void mel_finalize(const float* __restrict__ part_s, c
         }                                                                        \
     } while (0)
 
+// ---- frame loads ----------------------------------------------------------------------------------------
+// The loads of a frame are issued a few chunks ahead of their use (see the worker loop).  They are volatile asm so
+// that neither nvcc nor ptxas gathers them at the top of the frame again (64 live registers and an LSU queue that
+// back-pressures every shared-memory access behind it).
+__device__ __forceinline__ float4 ldg_nc_f4(const void* p) {
+    float4 v;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_nc_u4(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg_nc_u2(const void* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+
 // 4 consecutive sample frames of interleaved 16-bit PCM (C in {1, 2, 4}: 8 C bytes, aligned) -> mono floats.  The raw
-// load and the conversion are separate so that all loads of a batch are in flight before the first conversion waits.
+// load and the conversion are separate so that the loads stay in flight while earlier chunks are processed.
 __device__ __forceinline__ float s16lo(uint32_t w) { return static_cast<float>(static_cast<short>(w & 0xffffu)); }
 __device__ __forceinline__ float s16hi(uint32_t w) { return static_cast<float>(static_cast<int>(w) >> 16); }
 template <int C>
@@ -229,20 +275,23 @@ struct PcmRaw {
     uint32_t w[2 * C];
 };
 template <int C>
-__device__ __forceinline__ PcmRaw<C> pcm_load_raw(const int16_t* __restrict__ p, bool live) {
+__device__ __forceinline__ PcmRaw<C> pcm_zero_raw() {
     PcmRaw<C> r;
 #pragma unroll
     for (int i = 0; i < 2 * C; ++i) r.w[i] = 0u;
-    if (live) {
-        if (C == 1) {
-            const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
-            r.w[0] = v.x; r.w[1] = v.y;
-        } else {
+    return r;
+}
+template <int C>
+__device__ __forceinline__ PcmRaw<C> pcm_load_raw(const int16_t* __restrict__ p) {
+    PcmRaw<C> r;
+    if (C == 1) {
+        const uint2 v = ldg_nc_u2(p);
+        r.w[0] = v.x; r.w[1] = v.y;
+    } else {
 #pragma unroll
-            for (int q = 0; q < C / 2; ++q) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + q);
-                r.w[4 * q] = v.x; r.w[4 * q + 1] = v.y; r.w[4 * q + 2] = v.z; r.w[4 * q + 3] = v.w;
-            }
+        for (int q = 0; q < C / 2; ++q) {
+            const uint4 v = ldg_nc_u4(reinterpret_cast<const uint4*>(p) + q);
+            r.w[4 * q] = v.x; r.w[4 * q + 1] = v.y; r.w[4 * q + 2] = v.z; r.w[4 * q + 3] = v.w;
         }
     }
     return r;
@@ -261,30 +310,6 @@ __device__ __forceinline__ float4 pcm_to_mono4(const PcmRaw<C>& r, float scale) 
             v[e] = (s16lo(r.w[2 * e]) + s16hi(r.w[2 * e])) + (s16lo(r.w[2 * e + 1]) + s16hi(r.w[2 * e + 1]));
     }
     return make_float4(v[0] * scale, v[1] * scale, v[2] * scale, v[3] * scale);
-}
-// whole interior frame of this thread: 16 positions (xa[0..7], xb[0..7]) in batches of kBatch raw loads
-template <int C>
-__device__ __forceinline__ void pcm_load_frame(const int16_t* __restrict__ pa, const int16_t* __restrict__ pb,
-                                               const int16_t* __restrict__ pb0, bool live_a0, bool live_b0, float scale,
-                                               float4* xa, float4* xb) {
-    constexpr int kBatch = (C == 4) ? 4 : (C == 2 ? 8 : 16);
-    constexpr int rowc = 128 * 16 * C;                                      // 16 rows
-#pragma unroll
-    for (int b0 = 0; b0 < 16; b0 += kBatch) {
-        PcmRaw<C> raw[kBatch];
-#pragma unroll
-        for (int i = 0; i < kBatch; ++i) {
-            const int pos = b0 + i, c = pos & 7;
-            if (pos < 8) raw[i] = pcm_load_raw<C>(pa + rowc * c, c > 0 || live_a0);
-            else raw[i] = pcm_load_raw<C>(c == 0 ? pb0 : pb - rowc * c, c > 0 || live_b0);
-        }
-#pragma unroll
-        for (int i = 0; i < kBatch; ++i) {
-            const int pos = b0 + i;
-            if (pos < 8) xa[pos] = pcm_to_mono4<C>(raw[i], scale);
-            else xb[pos - 8] = pcm_to_mono4<C>(raw[i], scale);
-        }
-    }
 }
 
 constexpr int kInPcmAny = 16;   // IN value: 16-bit PCM with a run-time channel count (scalar loads)
@@ -322,6 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
     // log-mel mode: the two helper warps take the mel finalize off the workers
     uint64_t* part_full = bars + 17; // mel partial moments (and the frame's scale) are in shared memory (16 worker warps)
     uint64_t* part_free = bars + 18; // helpers have finished the previous frame's finalize
+    uint64_t* dec = bars + 19;       // fp16 build: the workers have decided whether the stage-1 attempt stands (redo flag in red_s[24])
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
@@ -338,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         mbar_init(b2_full, 1);
         mbar_init(part_full, kWorkerWarps);
         mbar_init(part_free, 2);
+        mbar_init(dec, 1);
         mbar_fence_init();
     }
     if (warp == kMmaWarp) tmem_alloc<512>(tmem_ptr_s);
@@ -363,10 +390,16 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr_s;
 
+    // Frame schedule: CTA b owns the CONSECUTIVE frames [f0, f0 + n_iter) of the flattened (clip, frame) sequence.  Two
+    // consecutive frames of a clip share half their samples (hop = window / 2), so the second read of a sample hits L2
+    // right after the first, and -- fp16 build -- the abs-max of the shared half is known before the frame is loaded,
+    // which lets the fold start on the first samples that arrive (see "block scale" in the worker loop).
     const long long total_frames = static_cast<long long>(prm.n_clips) * prm.n_frames;
-    const int n_iter = (blockIdx.x < total_frames)
-                           ? static_cast<int>((total_frames - blockIdx.x + gridDim.x - 1) / gridDim.x)
-                           : 0;
+    const long long per_cta = total_frames / gridDim.x;
+    const int rem_cta = static_cast<int>(total_frames - per_cta * gridDim.x);
+    const long long f0 = per_cta * blockIdx.x + min(static_cast<int>(blockIdx.x), rem_cta);
+    const int n_iter = static_cast<int>(per_cta) + (static_cast<int>(blockIdx.x) < rem_cta ? 1 : 0);
+    volatile int* redo_s = reinterpret_cast<volatile int*>(red_s + 24);
 
     // ======================================================================== bulk-copy producer warp
     // register re-allocation between warp groups: 4 service warps x 32 regs + 16 worker warps x 112 regs = the 96 x 640
@@ -381,7 +414,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
             const int hid = tid - (kWorkerWarps + 2) * 32;            // 0..63
             for (int it = 0; it < n_iter; ++it) {
                 mbar_wait(part_full, it & 1);
-                const long long f = blockIdx.x + static_cast<long long>(it) * gridDim.x;
+                const long long f = f0 + it;
                 float* out_row = prm.out + f * kMel;                  // (clip * T + t) * 64 = f * 64
                 const float inv_scale2 = red_s[20];
 #pragma unroll 1
@@ -400,12 +433,16 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 bulk_g2s(b2_s + a * kB2ArrBytes, prm.b2 + a * kB2ArrBytes, kB2ArrBytes, b2_full);
         }
         __syncwarp();
-        for (int it = 0; it < n_iter; ++it) {
+        // One pass over the 8 constant chunks per stage-1 ATTEMPT (8 chunks = two revolutions of the 4-slot ring, so slot
+        // and parity of chunk c are the same in every attempt).  fp16 build: a frame whose provisional block scale turns
+        // out too large is folded again (worker loop), which consumes another 8 chunks; the workers' decision arrives on
+        // `dec` right after the fold, long before the next frame needs its first constants.
+        int attempt = 0;
+        for (int it = 0; it < n_iter;) {
 #pragma unroll 1
             for (int c = 0; c < 8; ++c) {
-                const int g = it * 8 + c;
-                const int s = g & (kNumSlots - 1);
-                const int u = g / kNumSlots;
+                const int s = c & (kNumSlots - 1);
+                const int u = c / kNumSlots;
                 mbar_wait(&empty1[s], (u & 1) ^ 1);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&full1[s], kA1ChunkBytes);
@@ -413,27 +450,33 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 }
                 __syncwarp();
             }
-            // pull the next frame's samples towards L2 while this one is being processed
+            // pull the new half of the next frame towards L2 while this one is being processed (the other half is this
+            // frame's second half; a clip's first frame takes everything up to the end of its window)
             if (SEDB_L2_PREFETCH && it + 1 < n_iter) {
-                const long long f = blockIdx.x + static_cast<long long>(it + 1) * gridDim.x;
+                const long long f = f0 + it + 1;
                 const int clip = static_cast<int>(f / prm.n_frames);
                 const int t = static_cast<int>(f - static_cast<long long>(clip) * prm.n_frames);
-                const long long j0 = static_cast<long long>(t) * kHop + kLpad - kPadRefl;
-                const void* src;
-                uint32_t nbytes;
-                if (IN == 0) {
-                    src = prm.wave + static_cast<long long>(clip) * prm.wave_stride + j0;
-                    nbytes = kWin * 4;
-                } else {
-                    src = prm.pcm + (static_cast<long long>(clip) * prm.wave_stride + j0) * prm.n_channels;
-                    nbytes = kWin * 2 * prm.n_channels;
-                }
-                if (j0 >= 0 && j0 + kWin <= prm.n_samples && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+                const long long lo = (t == 0) ? 0 : static_cast<long long>(t) * kHop;
+                long long hi = static_cast<long long>(t) * kHop + kHop;
+                if (hi > prm.n_samples) hi = prm.n_samples;
+                const long long bytes_per = (IN == 0) ? 4 : 2 * prm.n_channels;
+                const char* src = (IN == 0)
+                    ? reinterpret_cast<const char*>(prm.wave + static_cast<long long>(clip) * prm.wave_stride + lo)
+                    : reinterpret_cast<const char*>(prm.pcm + (static_cast<long long>(clip) * prm.wave_stride + lo) * prm.n_channels);
+                const long long nbytes = ((hi - lo) * bytes_per) & ~15LL;
+                if (nbytes > 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
                     if (elect_one())
-                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(nbytes) : "memory");
+                        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(static_cast<uint32_t>(nbytes)) : "memory");
                     __syncwarp();
                 }
             }
+#if SEDB_SPLIT_FP16
+            mbar_wait(dec, attempt & 1);
+            ++attempt;
+            if (*redo_s == 0) ++it;
+#else
+            ++it;
+#endif
         }
     }
     // ======================================================================== MMA issuer warp
@@ -453,28 +496,40 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         constexpr uint32_t kA1Step = kA1ArrBytes >> 4, kB1Step = kB1ArrBytes >> 4;
         constexpr uint32_t kB2Step = kB2ArrBytes >> 4, kA1SlotStep = kA1ChunkBytes >> 4, kB1SlotStep = kB1SlotBytes >> 4;
         mbar_wait(b2_full, 0);
+        int attempt = 0;
         for (int it = 0; it < n_iter; ++it) {
-            // ---------------- stage 1: 8 K-chunks of 16 folded rows (m)
+            // ---------------- stage 1: 8 K-chunks of 16 folded rows (m); repeated when the workers reject the attempt
+            for (;;) {
 #pragma unroll 1
-            for (int c = 0; c < 8; ++c) {
-                const int g = it * 8 + c;
-                const int s = g & (kNumSlots - 1);
-                const int u = g / kNumSlots;
-                mbar_wait(&full1[s], u & 1);
-                tc_fence_after();
-                if (elect_one()) {
-                    const uint64_t a = dA1 + s * kA1SlotStep, bb = dB1 + s * kB1SlotStep;
-                    const uint32_t acc = (c > 0) ? 1u : 0u;
-                    umma_f16(0, a, bb, idesc1, acc);                                   // cH uH
-                    umma_f16(0, a + kA1Step, bb, idesc1, 1u);                          // cL uH
-                    umma_f16(0, a, bb + kB1Step, idesc1, 1u);                          // cH uL
-                    umma_f16(128, a + 2 * kA1Step, bb + 2 * kB1Step, idesc1, acc);     // sH vH
-                    umma_f16(128, a + 3 * kA1Step, bb + 2 * kB1Step, idesc1, 1u);      // sL vH
-                    umma_f16(128, a + 2 * kA1Step, bb + 3 * kB1Step, idesc1, 1u);      // sH vL
-                    umma_commit(&empty1[s]);
-                    if (c == 7) umma_commit(d1_full);
+                for (int c = 0; c < 8; ++c) {
+                    const int s = c & (kNumSlots - 1);
+                    const int u = c / kNumSlots;
+                    mbar_wait(&full1[s], u & 1);
+#if SEDB_CONSUMER_FENCE
+                    if (!SEDB_TAIL_FENCE || c < 7) fence_proxy_async_smem();
+#endif
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint64_t a = dA1 + s * kA1SlotStep, bb = dB1 + s * kB1SlotStep;
+                        const uint32_t acc = (c > 0) ? 1u : 0u;
+                        umma_f16(0, a, bb, idesc1, acc);                                   // cH uH
+                        umma_f16(0, a + kA1Step, bb, idesc1, 1u);                          // cL uH
+                        umma_f16(0, a, bb + kB1Step, idesc1, 1u);                          // cH uL
+                        umma_f16(128, a + 2 * kA1Step, bb + 2 * kB1Step, idesc1, acc);     // sH vH
+                        umma_f16(128, a + 3 * kA1Step, bb + 2 * kB1Step, idesc1, 1u);      // sL vH
+                        umma_f16(128, a + 2 * kA1Step, bb + 3 * kB1Step, idesc1, 1u);      // sH vL
+                        umma_commit(&empty1[s]);
+                        if (c == 7) umma_commit(d1_full);
+                    }
+                    __syncwarp();
                 }
-                __syncwarp();
+#if SEDB_SPLIT_FP16
+                mbar_wait(dec, attempt & 1);
+                ++attempt;
+                if (*redo_s == 0) break;
+#else
+                break;
+#endif
             }
             // ---------------- stage 2: 4 K-chunks of 16 columns (n), even and odd outputs; A operand from TMEM
 #pragma unroll 1
@@ -537,183 +592,364 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         const uint32_t b1_off = (lane >> 1) * kB1Sbo + (r >> 3) * kB1Lbo + (r & 7) * 16 + (lane & 1) * 8;
         const float alt_sign = (r & 1) ? -1.f : 1.f;
 
+        // shared-window address of the power spectrum, opaque to the optimiser so that it stays in a register
+        uint32_t p_s_addr;
+        asm volatile("mov.u32 %0, %1;" : "=r"(p_s_addr) : "r"(smem_u32(p_s)));
+        // raw form of four consecutive samples between the load and its use: the loaded words themselves
+        constexpr int PC = (IN == 1 || IN == 2 || IN == 4) ? IN : 0;          // vector PCM loader
+        using Raw = typename std::conditional<PC != 0, PcmRaw<(PC != 0 ? PC : 1)>, float4>::type;
+        constexpr int kAhead = (PC == 4) ? 1 : SEDB_KAHEAD;                                             // chunks in flight ahead of the fold
+
+        // fp16 build: exponent of the block scale that one half of a frame would get on its own: 2^e |x| < 64 with e
+        // rounded down to even (sqrt(scale) rides on the window factors); silence gets the largest scale
+        auto ebucket = [](float mx) -> int {
+            int e = 60;
+            if (mx > 0.f) e = 5 - (static_cast<int>((__float_as_uint(mx) >> 23) & 0xff) - 127);
+            if (!(mx < 3.0e38f)) e = 0;                                       // inf / nan: nothing to preserve
+            return max(-56, min(60, e)) & ~1;
+        };
+        auto absmax4 = [](float m, const float4& v) {
+            return fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+        };
+        int e_hist = 0;                         // ebucket of the previous frame's second half = this frame's first half
+        int attempt = 0;                        // stage-1 attempts so far (parity of d1_full / dec)
+
+        // ---------------------------------------------------------------- frame loader
+        // chunk c, this thread: rows m = 16 c + r (first half of the frame) and 256 - m (second half; row 128 for
+        // m = 0), samples n2 = 4 lane .. +3.  Interior frames (every in-window sample inside the clip, aligned rows:
+        // all but the first and last frames of a clip) load vectors off two base pointers; only chunk 0 touches rows
+        // that are partly outside the window.  Edge frames take the general path (reflect padding, scalar loads).
+        const int L = prm.n_samples;
+        const int na = 128 * r + 4 * lane, nb = 128 * (r == 0 ? 128 : 256 - r) + 4 * lane;
+        const bool live_a0 = na >= kLpad, live_b0 = nb < kLpad + kWin;
+        const int C = (IN == 0) ? 1 : (IN == kInPcmAny ? prm.n_channels : IN);
+        const float ps = prm.pcm_scale;
+        const int fbytes = (IN == 0) ? 4 : 2 * C;                               // bytes per sample frame
+        const int pb_off = 128 * (256 - 2 * r) * fbytes;                        // row 256 - r relative to row r, bytes
+
         long long tprev = clock64();
         for (int it = 0; it < n_iter; ++it) {
-            const long long f = blockIdx.x + static_cast<long long>(it) * gridDim.x;
+            const long long f = f0 + it;
             const int clip = static_cast<int>(f / prm.n_frames);
             const int t = static_cast<int>(f - static_cast<long long>(clip) * prm.n_frames);
-            const int L = prm.n_samples;
-
-            // ---------------------------------------------------------------- load the frame into registers
-            // chunk c, this thread: rows m = 16 c + r and 256 - m (row 128 for m = 0), samples n2 = 4 lane .. +3.
-            // Interior frames (every in-window sample inside the clip, aligned rows: all but the first and last frames
-            // of a clip) use straight-line vector loads off two base pointers; only chunk 0 touches rows that are partly
-            // outside the window.  Edge frames take the general path (reflect padding, scalar loads).
-            float4 xa[8], xb[8];
             const bool inside = t >= 1 && static_cast<long long>(t) * kHop + (kWin / 2) <= L;
-            const int na = 128 * r + 4 * lane, nb = 128 * (r == 0 ? 128 : 256 - r) + 4 * lane;
-            if (IN == 0) {
-                const float* __restrict__ y = prm.wave + static_cast<long long>(clip) * prm.wave_stride;
-                const bool vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0);
-                auto load4 = [&](int n0) -> float4 {
-                    const int j0 = t * kHop + n0 - kPadRefl;
-                    if (n0 < kLpad - 3 || n0 >= kLpad + kWin) return make_float4(0.f, 0.f, 0.f, 0.f);   // window is zero
-                    if (vec_ok && j0 >= 0 && j0 + 4 <= L) return __ldg(reinterpret_cast<const float4*>(y + j0));
+            const char* ybase;                                                  // clip start
+            if (IN == 0) ybase = reinterpret_cast<const char*>(prm.wave + static_cast<long long>(clip) * prm.wave_stride);
+            else ybase = reinterpret_cast<const char*>(prm.pcm + static_cast<long long>(clip) * prm.wave_stride * C);
+            const bool fast = inside && IN != kInPcmAny && ((reinterpret_cast<uintptr_t>(ybase) & 15) == 0);
+            // row r of the frame, this lane's samples (row 16 c + r: + 2048 c sample frames; row 256 - 16 c - r: pb_off - 2048 c)
+            const char* pa = ybase + (static_cast<long long>(t) * kHop - kPadRefl + 4 * lane + 128 * r) * fbytes;
+            // general path: 4 sample frames from frame position n0, zero outside the window, reflect outside the clip
+            auto load_general = [&](int n0) -> Raw {
+                // (opaque to the optimiser: otherwise the reflected addresses of all 64 scalar loads of an edge frame are
+                // formed at the top of the frame and spill the workers' registers in every frame)
+                asm volatile("" : "+r"(n0));
+                const int j0 = t * kHop + n0 - kPadRefl;
+                const bool dead = n0 < kLpad - 3 || n0 >= kLpad + kWin;           // window is zero
+                if constexpr (PC != 0) {
+                    Raw q = pcm_zero_raw<PC>();
+                    if (!dead) {
+                        const int16_t* y = reinterpret_cast<const int16_t*>(ybase);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int16_t* src = y + static_cast<long long>(reflect_index(j0 + e, L)) * PC;
+#pragma unroll
+                            for (int ch = 0; ch < PC; ++ch) {
+                                const uint32_t v = static_cast<uint16_t>(__ldg(src + ch));
+                                q.w[(e * PC + ch) >> 1] |= v << (16 * ((e * PC + ch) & 1));
+                            }
+                        }
+                    }
+                    return q;
+                } else if constexpr (IN == 0) {
+                    if (dead) return make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float* y = reinterpret_cast<const float*>(ybase);
+                    if (((reinterpret_cast<uintptr_t>(y) & 15) == 0) && j0 >= 0 && j0 + 4 <= L && (j0 & 3) == 0)
+                        return ldg_nc_f4(y + j0);
                     float4 v;
                     v.x = __ldg(y + reflect_index(j0 + 0, L));
                     v.y = __ldg(y + reflect_index(j0 + 1, L));
                     v.z = __ldg(y + reflect_index(j0 + 2, L));
                     v.w = __ldg(y + reflect_index(j0 + 3, L));
                     return v;
-                };
-                if (inside && vec_ok) {
-                    const float* fr = y + (static_cast<long long>(t) * kHop - kPadRefl) + 4 * lane;
-                    const float4* pa = reinterpret_cast<const float4*>(fr + 128 * r);             // row 16 c + r: + 512 c
-                    const float4* pb = reinterpret_cast<const float4*>(fr + 128 * (256 - r));     // row 256 - 16 c - r: - 512 c
-                    xa[0] = (na >= kLpad) ? __ldg(pa) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    xb[0] = (nb < kLpad + kWin) ? __ldg(r == 0 ? pb - 32 * 128 : pb) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-                    for (int c = 1; c < 8; ++c) {
-                        xa[c] = __ldg(pa + 512 * c);
-                        xb[c] = __ldg(pb - 512 * c);
-                    }
                 } else {
-#pragma unroll
-                    for (int c = 0; c < 8; ++c) {
-                        const int m = 16 * c + r;
-                        xa[c] = load4(128 * m + 4 * lane);
-                        xb[c] = load4(128 * ((m == 0) ? 128 : 256 - m) + 4 * lane);
-                    }
-                }
-            } else {
-                const int C = (IN == kInPcmAny) ? prm.n_channels : IN;           // compile-time for 1, 2, 4 channels
-                const float ps = prm.pcm_scale;
-                const int16_t* __restrict__ y = prm.pcm + static_cast<long long>(clip) * prm.wave_stride * C;
-                const bool vec_ok = ((reinterpret_cast<uintptr_t>(y) & 15) == 0) && IN != kInPcmAny;
-                auto load4 = [&](int n0) -> float4 {
-                    const int j0 = t * kHop + n0 - kPadRefl;
-                    if (n0 < kLpad - 3 || n0 >= kLpad + kWin) return make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (dead) return make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int16_t* y = reinterpret_cast<const int16_t*>(ybase);
                     float v[4];
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
-                        const int16_t* q = y + static_cast<long long>(reflect_index(j0 + e, L)) * C;
+                        const int16_t* src = y + static_cast<long long>(reflect_index(j0 + e, L)) * C;
                         int acc = 0;
-                        for (int ch = 0; ch < C; ++ch) acc += __ldg(q + ch);
+                        for (int ch = 0; ch < C; ++ch) acc += __ldg(src + ch);
                         v[e] = static_cast<float>(acc) * ps;
                     }
                     return make_float4(v[0], v[1], v[2], v[3]);
-                };
-                if (inside && vec_ok) {
-                    const int16_t* fr = y + (static_cast<long long>(t) * kHop - kPadRefl + 4 * lane) * C;
-                    const int16_t* pa = fr + 128 * r * C;
-                    const int16_t* pb = fr + 128 * (256 - r) * C;
-                    const int16_t* pb0 = (r == 0) ? pb - 128 * 128 * C : pb;
-                    const bool la = na >= kLpad, lb = nb < kLpad + kWin;
-                    if constexpr (IN == 1 || IN == 2 || IN == 4) pcm_load_frame<IN>(pa, pb, pb0, la, lb, ps, xa, xb);
-                } else {
+                }
+            };
+            auto load_vec = [&](const char* p) -> Raw {
+                if constexpr (PC != 0) return pcm_load_raw<PC>(reinterpret_cast<const int16_t*>(p));
+                else return ldg_nc_f4(p);
+            };
+            auto zero_raw = [&]() -> Raw {
+                if constexpr (PC != 0) return pcm_zero_raw<PC>();
+                else return make_float4(0.f, 0.f, 0.f, 0.f);
+            };
+            // fast path (c is a compile-time constant at every call)
+            auto load_a = [&](int c) -> Raw {
+                if (c == 0 && !live_a0) return zero_raw();
+                return load_vec(pa + static_cast<long long>(2048 * c) * fbytes);
+            };
+            auto load_b = [&](int c) -> Raw {
+                const char* pb = pa + pb_off;
+                if (c == 0) return live_b0 ? load_vec(r == 0 ? pb - static_cast<long long>(128 * 128) * fbytes : pb) : zero_raw();
+                return load_vec(pb - static_cast<long long>(2048 * c) * fbytes);
+            };
+            // general path (edge frames, unaligned clips, run-time channel counts): a compact loop over the chunks
+            auto load_a_gen = [&](int c) -> Raw { return load_general(128 * (16 * c + r) + 4 * lane); };
+            auto load_b_gen = [&](int c) -> Raw {
+                const int m = 16 * c + r;
+                return load_general(128 * ((m == 0) ? 128 : 256 - m) + 4 * lane);
+            };
+            auto cvt = [&](const Raw& q) -> float4 {
+                if constexpr (PC != 0) return pcm_to_mono4<PC>(q, ps);
+                else return q;
+            };
+
+            // ---------------------------------------------------------------- block scale (fp16 halves)
+            // The scale 2^e must keep 2^e |x| < 64 over the whole frame (then no intermediate exceeds 2^15 < 65504) without
+            // wasting more than a few binades.  It is a function of the frame's own samples only, chosen so that it is
+            // usually known BEFORE the frame is loaded: with eA / eB the exponents the first / second half would get on
+            // their own,   e = eA - 2 if eB >= eA - 2 (the second half is not more than ~12 dB louder), else e = eB.
+            // The first half of a frame is the second half of the previous frame of the clip, which this CTA has just
+            // processed, so eA is known; the fold runs with eA - 2 while the samples arrive and tracks the abs-max of the
+            // second half; if that breaks the condition the stage-1 attempt is dropped and repeated with eB.  Frames
+            // without history (first of the CTA or of a clip) find both maxima in a pass of their own first.
+            int e = 0, eB = 0;
+            bool provisional = false;
+#if SEDB_SPLIT_FP16
+            if (it > 0 && t >= 1) {
+                e = max(-56, e_hist - 2);
+                provisional = true;
+            } else {
+                float mA = 0.f, mB = 0.f;
+                if (fast) {
 #pragma unroll
+                    for (int c0 = 0; c0 < 8; c0 += 4) {                          // two batches: rare path, few registers
+                        Raw qa[4], qb[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            qa[c] = load_a(c0 + c);
+                            qb[c] = load_b(c0 + c);
+                        }
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            mA = absmax4(mA, cvt(qa[c]));
+                            mB = absmax4(mB, cvt(qb[c]));
+                        }
+                    }
+                } else {
+#pragma unroll 1
                     for (int c = 0; c < 8; ++c) {
-                        const int m = 16 * c + r;
-                        xa[c] = load4(128 * m + 4 * lane);
-                        xb[c] = load4(128 * ((m == 0) ? 128 : 256 - m) + 4 * lane);
+                        mA = absmax4(mA, cvt(load_a_gen(c)));
+                        mB = absmax4(mB, cvt(load_b_gen(c)));
                     }
                 }
-            }
-            // ---------------------------------------------------------------- per-frame block scale (fp16 halves)
-            float scale = 1.0f, inv_scale = 1.0f, sqrt_scale = 1.0f;
-#if SEDB_SPLIT_FP16
-            {
-                float mx = 0.f;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(xa[c].x), fabsf(xa[c].y)), fmaxf(fabsf(xa[c].z), fabsf(xa[c].w))));
-                    mx = fmaxf(mx, fmaxf(fmaxf(fabsf(xb[c].x), fabsf(xb[c].y)), fmaxf(fabsf(xb[c].z), fabsf(xb[c].w))));
+                for (int o = 16; o > 0; o >>= 1) {
+                    mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, o));
+                    mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, o));
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                if (lane == 0) red_s[warp] = mx;
+                if (lane == 0) {
+                    red_s[warp] = mB;
+                    red_s[32 + warp] = mA;
+                }
                 worker_sync();
-                mx = red_s[lane & 15];
+                mA = red_s[32 + (lane & 15)];
+                mB = red_s[lane & 15];
 #pragma unroll
-                for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-                // scale = 2^e, e = 5 - floor(log2 max) rounded down to even: |x| scale < 64, so no intermediate can
-                // exceed 2^15 < 65504; sqrt(scale) rides on the window factors
-                int e = 0;
-                if (mx > 0.f && mx < 3.0e38f) e = 5 - (static_cast<int>((__float_as_uint(mx) >> 23) & 0xff) - 127);
-                e = max(-56, min(60, e)) & ~1;
-                scale = __uint_as_float(static_cast<uint32_t>(127 + e) << 23);
-                inv_scale = __uint_as_float(static_cast<uint32_t>(127 - e) << 23);
-                sqrt_scale = __uint_as_float(static_cast<uint32_t>(127 + e / 2) << 23);
+                for (int o = 8; o > 0; o >>= 1) {
+                    mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, o));
+                    mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, o));
+                }
+                const int eA = ebucket(mA);
+                eB = ebucket(mB);
+                const int ep = max(-56, eA - 2);
+                e = (eB >= ep) ? ep : eB;
             }
 #endif
-            SEDB_PROF(0);   // frame load (+ block scale)
-            // ---------------------------------------------------------------- stage 1: window, fold, split
-            float2 alt01 = f2s(0.f), alt23 = f2s(0.f);
-            // window w = sin^2(phi_m + phi_n2) from the factor tables (no per-frame window traffic from L2); packed fp32
-            // arithmetic throughout (two samples per instruction)
-            const float4 hc = *reinterpret_cast<const float4*>(hlane_s + 4 * lane);
-            const float4 hs = *reinterpret_cast<const float4*>(hlane_s + 128 + 4 * lane);
-            const float2 hc01 = f2(hc.x, hc.y), hc23 = f2(hc.z, hc.w), hs01 = f2(hs.x, hs.y), hs23 = f2(hs.z, hs.w);
+#ifdef SEDB_DEBUG_SCALE
+            if (tid == 0) printf("SCALE f %lld t %d fast %d prov %d e %d eB %d\n", f, t, int(fast), int(provisional), e, eB);
+#endif
+            float scale, inv_scale;
+            for (;;) {                                                          // stage-1 attempts (one, except after a rejected scale)
+                scale = __uint_as_float(static_cast<uint32_t>(127 + e) << 23);
+                inv_scale = __uint_as_float(static_cast<uint32_t>(127 - e) << 23);
+                const float sqrt_scale = __uint_as_float(static_cast<uint32_t>(127 + e / 2) << 23);
+                // ------------------------------------------------------------ stage 1: load, window, fold, split
+                Raw qa[8], qb[8];
+                if (fast) {
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                const int g = it * 8 + c;
-                const int s = g % kNumSlots;
-                const int u = g / kNumSlots;
-                const int m = 16 * c + r;
-                float2 ra = hrow_s[m], rb = hrow_s[m == 0 ? 128 : 256 - m];
-                ra.x *= sqrt_scale; ra.y *= sqrt_scale; rb.x *= sqrt_scale; rb.y *= sqrt_scale;
-                auto win2 = [](float2 x, float2 rw, float2 cn, float2 sn) {
-                    const float2 t = f2fma(f2s(rw.y), sn, f2mul(f2s(rw.x), cn));   // sqrt(scale) sin(phi_m + phi_n2)
-                    return f2mul(x, f2mul(t, t));
-                };
-                const float2 a01 = win2(f2(xa[c].x, xa[c].y), ra, hc01, hs01);
-                const float2 a23 = win2(f2(xa[c].z, xa[c].w), ra, hc23, hs23);
-                const float2 b01 = win2(f2(xb[c].x, xb[c].y), rb, hc01, hs01);
-                const float2 b23 = win2(f2(xb[c].z, xb[c].w), rb, hc23, hs23);
-                float2 u01, u23, v01, v23;
-                if (m == 0) {                                   // warp-uniform: U[0] = X[0], V[0] = 0, keep X[128]
-                    u01 = a01; u23 = a23;
-                    v01 = v23 = f2s(0.f);
-                    *reinterpret_cast<float4*>(x128_s + 4 * lane) = make_float4(b01.x, b01.y, b23.x, b23.y);
-                } else {
-                    u01 = f2add(a01, b01); u23 = f2add(a23, b23);
-                    v01 = f2sub(a01, b01); v23 = f2sub(a23, b23);
+                    for (int c = 0; c < kAhead; ++c) {
+                        qa[c] = load_a(c);
+                        qb[c] = load_b(c);
+                    }
                 }
-                alt01 = f2add(alt01, u01);
-                alt23 = f2add(alt23, u23);
-                uint32_t uh[2], ul[2], vh[2], vl[2];
-                split_pack2(u01, uh[0], ul[0]);
-                split_pack2(u23, uh[1], ul[1]);
-                split_pack2(v01, vh[0], vl[0]);
-                split_pack2(v23, vh[1], vl[1]);
-                mbar_wait(&empty1[s], (u & 1) ^ 1);
-                uint8_t* dst = b1ring + s * kB1SlotBytes + b1_off;
-                *reinterpret_cast<uint2*>(dst + 0 * kB1ArrBytes) = make_uint2(uh[0], uh[1]);
-                *reinterpret_cast<uint2*>(dst + 1 * kB1ArrBytes) = make_uint2(ul[0], ul[1]);
-                *reinterpret_cast<uint2*>(dst + 2 * kB1ArrBytes) = make_uint2(vh[0], vh[1]);
-                *reinterpret_cast<uint2*>(dst + 3 * kB1ArrBytes) = make_uint2(vl[0], vl[1]);
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full1[s]);
+                // the previous frame's mel partial sums read the power spectrum, which aliases the operand ring
+                worker_sync();
+                SEDB_PROF(0);   // frame setup (+ the abs-max pass of a frame without history)
+                float2 alt01 = f2s(0.f), alt23 = f2s(0.f);
+                float mB = 0.f;
+                // window factors of this thread's four columns
+                const float4 hc = *reinterpret_cast<const float4*>(hlane_s + 4 * lane);
+                const float4 hs = *reinterpret_cast<const float4*>(hlane_s + 128 + 4 * lane);
+                // (sqrt(scale) is a power of two: scaling the column factors once is bit-identical to scaling every row factor)
+                const float2 sq2 = f2s(sqrt_scale);
+                const float2 hc01 = f2mul(sq2, f2(hc.x, hc.y)), hc23 = f2mul(sq2, f2(hc.z, hc.w));
+                const float2 hs01 = f2mul(sq2, f2(hs.x, hs.y)), hs23 = f2mul(sq2, f2(hs.z, hs.w));
+                // row factors, fetched one chunk ahead of their use
+#if SEDB_HROW_PIPE
+                float2 ra_nx = hrow_s[r], rb_nx = hrow_s[r == 0 ? 128 : 256 - r];
+#endif
+                // one chunk: window, even/odd fold, hi/lo split, operand store.  Window w = sin^2(phi_m + phi_n2) from the
+                // factor tables (no per-frame window traffic from L2); packed fp32 arithmetic throughout
+                auto fold_chunk = [&](int c, float4 xa, float4 xb) {
+#ifdef SEDB_PROF_FOLD
+                    long long tq0 = clock64();
+                    asm volatile("mov.b32 %0, %0;\n\tmov.b32 %1, %1;" : "+f"(xa.x), "+f"(xb.x));
+                    if (prm.prof != nullptr && tid == 0) atomicAdd(prm.prof + 12, static_cast<unsigned long long>(clock64() - tq0));
+#endif
+                    const int s = c % kNumSlots;
+                    const int u = c / kNumSlots;
+                    const int m = 16 * c + r;
+                    mB = absmax4(mB, xb);
+#if SEDB_HROW_PIPE
+                    const float2 ra = ra_nx, rb = rb_nx;
+                    if (c < 7) {
+                        ra_nx = hrow_s[m + 16];
+                        rb_nx = hrow_s[240 - m];                    // 256 - (m + 16)
+                    }
+#else
+                    const float2 ra = hrow_s[m], rb = hrow_s[m == 0 ? 128 : 256 - m];
+#endif
+                    // window weight pair scale * sin^2(phi_m + phi_n2)
+                    auto win2 = [](float2 rw, float2 cn, float2 sn) {
+                        const float2 t = f2fma(f2s(rw.y), sn, f2mul(f2s(rw.x), cn));
+                        return f2mul(t, t);
+                    };
+                    // U = a wa + b wb, V = a wa - b wb with the second product fused into the add, written out so that
+                    // the two instances of this code (unrolled / edge-frame loop) cannot be contracted differently: a
+                    // clip's result must not depend on its alignment or its place in the batch
+                    const float2 wb01 = win2(rb, hc01, hs01), wb23 = win2(rb, hc23, hs23);
+                    const float2 a01 = f2mul(f2(xa.x, xa.y), win2(ra, hc01, hs01));
+                    const float2 a23 = f2mul(f2(xa.z, xa.w), win2(ra, hc23, hs23));
+                    const float2 xb01 = f2(xb.x, xb.y), xb23 = f2(xb.z, xb.w);
+                    float2 u01, u23, v01, v23;
+                    if (m == 0) {                                   // warp-uniform: U[0] = X[0], V[0] = 0, keep X[128]
+                        u01 = a01; u23 = a23;
+                        v01 = v23 = f2s(0.f);
+                        const float2 b01 = f2mul(xb01, wb01), b23 = f2mul(xb23, wb23);
+                        *reinterpret_cast<float4*>(x128_s + 4 * lane) = make_float4(b01.x, b01.y, b23.x, b23.y);
+                    } else {
+                        u01 = f2fma(xb01, wb01, a01); u23 = f2fma(xb23, wb23, a23);
+                        v01 = f2fma(f2neg(xb01), wb01, a01); v23 = f2fma(f2neg(xb23), wb23, a23);
+                    }
+                    alt01 = f2add(alt01, u01);
+                    alt23 = f2add(alt23, u23);
+                    uint32_t uh[2], ul[2], vh[2], vl[2];
+                    split_pack2(u01, uh[0], ul[0]);
+                    split_pack2(u23, uh[1], ul[1]);
+                    split_pack2(v01, vh[0], vl[0]);
+                    split_pack2(v23, vh[1], vl[1]);
+#ifdef SEDB_PROF_FOLD
+                    tq0 = clock64();
+#endif
+                    mbar_wait(&empty1[s], (u & 1) ^ 1);
+#ifdef SEDB_PROF_FOLD
+                    if (prm.prof != nullptr && tid == 0) atomicAdd(prm.prof + 13, static_cast<unsigned long long>(clock64() - tq0));
+                    tq0 = clock64();
+#endif
+                    uint8_t* dst = b1ring + s * kB1SlotBytes + b1_off;
+                    *reinterpret_cast<uint2*>(dst + 0 * kB1ArrBytes) = make_uint2(uh[0], uh[1]);
+                    *reinterpret_cast<uint2*>(dst + 1 * kB1ArrBytes) = make_uint2(ul[0], ul[1]);
+                    *reinterpret_cast<uint2*>(dst + 2 * kB1ArrBytes) = make_uint2(vh[0], vh[1]);
+                    *reinterpret_cast<uint2*>(dst + 3 * kB1ArrBytes) = make_uint2(vl[0], vl[1]);
+#if !SEDB_CONSUMER_FENCE
+                    fence_proxy_async_smem();
+#elif SEDB_TAIL_FENCE
+                    if (c == 7) fence_proxy_async_smem();             // last chunk: keep the fence off the MMA warp's tail
+#endif
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full1[s]);
+#ifdef SEDB_PROF_FOLD
+                    if (prm.prof != nullptr && tid == 0) atomicAdd(prm.prof + 14, static_cast<unsigned long long>(clock64() - tq0));
+#endif
+                };
+                if (fast) {
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        if (c + kAhead < 8) {
+                            qa[c + kAhead] = load_a(c + kAhead);
+                            qb[c + kAhead] = load_b(c + kAhead);
+                        }
+                        fold_chunk(c, cvt(qa[c]), cvt(qb[c]));
+                    }
+                } else {                                              // edge frames: a compact loop
+#pragma unroll 1
+                    for (int c = 0; c < 8; ++c) {
+                        const Raw a = load_a_gen(c), b = load_b_gen(c);
+                        fold_chunk(c, cvt(a), cvt(b));
+                    }
+                }
+                // alternating row sums for k1 = 128: row r of every chunk has parity r
+                *reinterpret_cast<float4*>(alt_s + r * 128 + 4 * lane) =
+                    make_float4(alt_sign * alt01.x, alt_sign * alt01.y, alt_sign * alt23.x, alt_sign * alt23.y);
+#if SEDB_SPLIT_FP16
+                if (provisional) {
+                    // non-negative floats order like their bit patterns: one REDUX instead of a shuffle tree
+                    const uint32_t mw = __reduce_max_sync(0xffffffffu, __float_as_uint(mB));
+                    if (lane == 0) red_s[warp] = __uint_as_float(mw);
+                }
+#endif
+                SEDB_PROF(1);   // load / fold / split / store
+                worker_sync();                                        // x128_s / alt_s (/ red_s) visible to all workers
+#if SEDB_SPLIT_FP16
+                bool redo = false;
+                if (provisional) {
+                    mB = red_s[lane & 15];
+#pragma unroll
+                    for (int o = 8; o > 0; o >>= 1) mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, o));
+                    eB = ebucket(mB);
+                    redo = eB < e;
+                }
+                if (tid == 0) {
+                    *redo_s = redo ? 1 : 0;
+                    mbar_arrive(dec);                                 // release: the MMA and copy warps read the flag
+                }
+                if (!redo) break;
+                mbar_wait(d1_full, attempt & 1);                      // the rejected attempt's MMAs (every phase is consumed)
+                ++attempt;
+                e = eB;
+                provisional = false;
+#else
+                break;
+#endif
             }
-            // alternating row sums for k1 = 128: row r of every chunk has parity r
-            *reinterpret_cast<float4*>(alt_s + r * 128 + 4 * lane) =
-                make_float4(alt_sign * alt01.x, alt_sign * alt01.y, alt_sign * alt23.x, alt_sign * alt23.y);
+            e_hist = eB;
 
-            SEDB_PROF(1);   // fold / split / store
             // ---------------------------------------------------------------- twiddle, radix-2, stage-2 A operand
             // (the row-128 input Y[n2,128] only needs the fold's partial sums: formed while the last stage-1 MMAs drain)
-            worker_sync();                                            // x128_s / alt_s visible to all workers
             if (tid < 128) {
                 float acc = x128_s[tid];
 #pragma unroll
                 for (int rr = 0; rr < 16; ++rr) acc += alt_s[rr * 128 + tid];
                 v_s[tid] = acc;                                       // Y[n2,128] (scaled)
             }
-            mbar_wait(d1_full, it & 1);
+            mbar_wait(d1_full, attempt & 1);
+            ++attempt;
             tc_fence_after();
             SEDB_PROF(2);   // wait for stage-1 MMAs
-#pragma unroll 1
+            constexpr int kTwUnroll = SEDB_TW_UNROLL;
+#pragma unroll kTwUnroll
             for (int c = 0; c < 4; ++c) {
                 // chunk c = columns n in [16 c, 16 c + 16) (and n + 64); this thread owns n = na + {0, 1, 8, 9}.
                 // The stage-2 A operand goes back into the very TMEM columns the thread has just read (two K elements
@@ -828,17 +1064,35 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                             pw[i + 1] = q.y;
                         }
                     }
+                    if (MODE == 0) {
+                        // bin of element i: k = kb + 512 i, stored at k (k2 < 64) or at the Hermitian mirror 32768 - k; the
+                        // column k1 = 0 has no mirror except the Nyquist bin.  Explicit shared-window addresses with
+                        // immediate offsets (as `p_s[bin]` under a branch ptxas re-derives the window base for every store)
+                        const int kb = k1 + 256 * par + 512 * j0;
+                        if (!mirrored) {
+                            const uint32_t a0 = p_s_addr + 4u * static_cast<uint32_t>(kb);
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int k = k1 + 256 * (2 * (j0 + i) + par);
-                        int bin;
-                        float sgn = 1.f;
-                        if (!mirrored) bin = k;
-                        else if (k1 >= 1) { bin = kNfft - k; sgn = -1.f; }        // Hermitian mirror (conjugate)
-                        else bin = (k == kNfft / 2) ? k : -1;
-                        if (bin >= 0) {
-                            if (MODE == 0) p_s[bin] = pw[i];
-                            else spec_row[bin] = make_float2(re[i] * inv_scale, sgn * im[i] * inv_scale);
+                            for (int i = 0; i < 8; ++i)
+                                asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0 + 2048u * i), "f"(pw[i]) : "memory");
+                        } else {
+                            const uint32_t a0 = p_s_addr + 4u * static_cast<uint32_t>(kNfft - kb);
+                            const bool nyq = (par == 0 && j0 == 32);          // k = 16384 for i = 0 in the column k1 = 0
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                if (k1 >= 1 || (i == 0 && nyq))
+                                    asm volatile("st.shared.f32 [%0], %1;" ::"r"(a0 - 2048u * i), "f"(pw[i]) : "memory");
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int k = k1 + 256 * (2 * (j0 + i) + par);
+                            int bin;
+                            float sgn = 1.f;
+                            if (!mirrored) bin = k;
+                            else if (k1 >= 1) { bin = kNfft - k; sgn = -1.f; }        // Hermitian mirror (conjugate)
+                            else bin = (k == kNfft / 2) ? k : -1;
+                            if (bin >= 0) spec_row[bin] = make_float2(re[i] * inv_scale, sgn * im[i] * inv_scale);
                         }
                     }
                 }

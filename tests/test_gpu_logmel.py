@@ -206,3 +206,46 @@ def test_dynamic_range_contract_two_sources():
         assert inside < TOL_DB
         if must_hold and DYN_RANGE_DB >= 100.0:
             assert err_quiet < TOL_DB
+
+
+def _level_steps(n, levels, seed=0):
+    """White noise whose level jumps between hop-aligned blocks (0 = digital silence)."""
+    rng = np.random.default_rng(77 + seed)
+    y = rng.standard_normal(n)
+    hop = 15840
+    for i in range(0, n, hop):
+        y[i:i + hop] *= levels[(i // hop) % len(levels)]
+    return np.clip(y, -1.0, 1.0)
+
+
+@pytest.mark.parametrize("levels", [
+    (1e-4, 1e-4, 0.3, 0.3, 1e-4),             # onsets of +70 dB: the provisional block scale is rejected and the frame refolded
+    (0.0, 0.0, 0.2, 0.0, 1e-3, 0.25),         # digital silence on either side of sound
+    (0.02, 0.09, 0.02, 0.005, 0.3),           # jumps around the acceptance threshold (12 dB) in both directions
+    (0.25, 1e-5, 1e-5, 1e-5),                 # a frame 88 dB below the previous one keeps its own scale
+])
+def test_block_scale_rule_on_level_steps(levels):
+    """fp16 build: the per-frame block scale is usually taken from the half the frame shares with its predecessor
+    (known before the frame is loaded); a louder second half makes the kernel drop the stage-1 attempt and fold the
+    frame again (csrc/logmel.cuh, "block scale").  Parity must not depend on which way a frame went."""
+    n = 15840 * 24 + 3000
+    y = _level_steps(n, levels)
+    out, ref = gpu_logmel(y), R.waveform_to_log_mel(y)
+    assert out.shape == ref.shape
+    assert_parity(out, ref)
+    live = ref > -99.0                       # bins of silent frames sit at the amin floor of power_to_db (-100 dB)
+    assert np.abs(out - ref)[live].max() < TOL_DB
+
+
+def test_result_independent_of_batch_position():
+    """A clip's log-mel must be bit-identical whatever batch it arrives in and wherever it sits in it: the frames are
+    dealt to the SMs in consecutive runs whose boundaries depend on the batch, and a run's first frame finds its block
+    scale by a pass of its own instead of from the previous frame; both ways must pick the same scale."""
+    clip = _level_steps(15840 * 40 + 123, (0.05, 0.3, 0.3, 1e-3, 0.0, 0.1), seed=3)
+    alone = gpu_logmel(clip[None])[0]
+    rng = np.random.default_rng(5)
+    for B, pos in [(3, 0), (3, 2), (7, 3), (150, 77)]:
+        batch = (rng.standard_normal((B, clip.size)) * 0.1).astype(np.float32)
+        batch[pos] = clip
+        got = gpu_logmel(batch)[pos]
+        assert np.array_equal(got, alone), (B, pos, np.abs(got - alone).max())
