@@ -42,6 +42,12 @@
 #ifndef SEDB_TW_UNROLL
 #define SEDB_TW_UNROLL 2
 #endif
+#ifndef SEDB_RELAX_NS
+#define SEDB_RELAX_NS 200
+#endif
+#ifndef SEDB_INCR_FRAME
+#define SEDB_INCR_FRAME 0
+#endif
 #ifndef SEDB_KAHEAD
 #define SEDB_KAHEAD 2
 #endif
@@ -413,7 +419,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         if (MODE == 0) {
             const int hid = tid - (kWorkerWarps + 2) * 32;            // 0..63
             for (int it = 0; it < n_iter; ++it) {
-                mbar_wait(part_full, it & 1);
+                mbar_wait_relaxed(part_full, it & 1, SEDB_RELAX_NS);
                 const long long f = f0 + it;
                 float* out_row = prm.out + f * kMel;                  // (clip * T + t) * 64 = f * 64
                 const float inv_scale2 = red_s[20];
@@ -443,7 +449,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
             for (int c = 0; c < 8; ++c) {
                 const int s = c & (kNumSlots - 1);
                 const int u = c / kNumSlots;
-                mbar_wait(&empty1[s], (u & 1) ^ 1);
+                mbar_wait_relaxed(&empty1[s], (u & 1) ^ 1, SEDB_RELAX_NS);
                 if (elect_one()) {
                     mbar_arrive_expect_tx(&full1[s], kA1ChunkBytes);
                     bulk_g2s(a1ring + s * kA1ChunkBytes, prm.a1 + c * kA1ChunkBytes, kA1ChunkBytes, &full1[s]);
@@ -471,7 +477,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 }
             }
 #if SEDB_SPLIT_FP16
-            mbar_wait(dec, attempt & 1);
+            mbar_wait_relaxed(dec, attempt & 1, SEDB_RELAX_NS);
             ++attempt;
             if (*redo_s == 0) ++it;
 #else
@@ -628,10 +634,21 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         const int pb_off = 128 * (256 - 2 * r) * fbytes;                        // row 256 - r relative to row r, bytes
 
         long long tprev = clock64();
+#if SEDB_INCR_FRAME
+        int clip = static_cast<int>(f0 / prm.n_frames);
+        int t = static_cast<int>(f0 - static_cast<long long>(clip) * prm.n_frames) - 1;
+#endif
         for (int it = 0; it < n_iter; ++it) {
+#if SEDB_INCR_FRAME
+            if (++t == prm.n_frames) {                                          // (no 64-bit division per frame)
+                t = 0;
+                ++clip;
+            }
+#else
             const long long f = f0 + it;
             const int clip = static_cast<int>(f / prm.n_frames);
             const int t = static_cast<int>(f - static_cast<long long>(clip) * prm.n_frames);
+#endif
             const bool inside = t >= 1 && static_cast<long long>(t) * kHop + (kWin / 2) <= L;
             const char* ybase;                                                  // clip start
             if (IN == 0) ybase = reinterpret_cast<const char*>(prm.wave + static_cast<long long>(clip) * prm.wave_stride);
@@ -716,19 +733,19 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
             };
 
             // ---------------------------------------------------------------- block scale (fp16 halves)
-            // The scale 2^e must keep 2^e |x| < 64 over the whole frame (then no intermediate exceeds 2^15 < 65504) without
-            // wasting more than a few binades.  It is a function of the frame's own samples only, chosen so that it is
-            // usually known BEFORE the frame is loaded: with eA / eB the exponents the first / second half would get on
-            // their own,   e = eA - 2 if eB >= eA - 2 (the second half is not more than ~12 dB louder), else e = eB.
-            // The first half of a frame is the second half of the previous frame of the clip, which this CTA has just
-            // processed, so eA is known; the fold runs with eA - 2 while the samples arrive and tracks the abs-max of the
-            // second half; if that breaks the condition the stage-1 attempt is dropped and repeated with eB.  Frames
-            // without history (first of the CTA or of a clip) find both maxima in a pass of their own first.
+            // The scale 2^e keeps 2^e |x| < 64 over the whole frame (then no intermediate exceeds 2^15 < 65504) with e the
+            // largest even exponent that does: a function of the frame's abs-max alone, e = min(eA, eB) with eA / eB the
+            // exponents its first / second half would get on their own.  The first half of a frame is the second half of
+            // the previous frame of the clip, which this CTA has just processed, so eA is known BEFORE the frame is
+            // loaded: the fold runs with eA on the samples as they arrive and tracks the abs-max of the second half; if
+            // that half turns out louder (eB < eA: an onset that crosses a scale step) the stage-1 attempt is dropped and
+            // repeated with eB.  Frames without history (first of the CTA or of a clip) find both maxima in a pass of
+            // their own first.  Either way the frame gets the same scale, so the result does not depend on the route.
             int e = 0, eB = 0;
             bool provisional = false;
 #if SEDB_SPLIT_FP16
             if (it > 0 && t >= 1) {
-                e = max(-56, e_hist - 2);
+                e = e_hist;
                 provisional = true;
             } else {
                 float mA = 0.f, mB = 0.f;
@@ -771,14 +788,12 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                     mA = fmaxf(mA, __shfl_xor_sync(0xffffffffu, mA, o));
                     mB = fmaxf(mB, __shfl_xor_sync(0xffffffffu, mB, o));
                 }
-                const int eA = ebucket(mA);
                 eB = ebucket(mB);
-                const int ep = max(-56, eA - 2);
-                e = (eB >= ep) ? ep : eB;
+                e = min(ebucket(mA), eB);
             }
 #endif
 #ifdef SEDB_DEBUG_SCALE
-            if (tid == 0) printf("SCALE f %lld t %d fast %d prov %d e %d eB %d\n", f, t, int(fast), int(provisional), e, eB);
+            if (tid == 0) printf("SCALE f %lld t %d fast %d prov %d e %d eB %d\n", f0 + it, t, int(fast), int(provisional), e, eB);
 #endif
             float scale, inv_scale;
             for (;;) {                                                          // stage-1 attempts (one, except after a rejected scale)

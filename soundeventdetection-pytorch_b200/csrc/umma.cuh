@@ -97,6 +97,27 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// The same for a warp that can afford to react late (producers that run ahead, helpers with a frame of slack): sleeps
+// between probes, so that the polling loop does not take issue slots from the working warps of its scheduler (a bare
+// try_wait loop issues an instruction every ~10 cycles: measured ~10 % of a scheduler's slots per polling warp).
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, uint32_t sleep_ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t spins = 0;
+    long long t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(sleep_ns);
+        if ((++spins & 0xffu) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 6000000000LL) {
+                printf("sedb: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
+                       smem_u32(bar), parity);
+                __trap();
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------ proxy fences
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() {

@@ -221,13 +221,13 @@ def _level_steps(n, levels, seed=0):
 @pytest.mark.parametrize("levels", [
     (1e-4, 1e-4, 0.3, 0.3, 1e-4),             # onsets of +70 dB: the provisional block scale is rejected and the frame refolded
     (0.0, 0.0, 0.2, 0.0, 1e-3, 0.25),         # digital silence on either side of sound
-    (0.02, 0.09, 0.02, 0.005, 0.3),           # jumps around the acceptance threshold (12 dB) in both directions
+    (0.02, 0.09, 0.02, 0.005, 0.3),           # jumps across one and several scale steps (a step = 12 dB) in both directions
     (0.25, 1e-5, 1e-5, 1e-5),                 # a frame 88 dB below the previous one keeps its own scale
 ])
 def test_block_scale_rule_on_level_steps(levels):
-    """fp16 build: the per-frame block scale is usually taken from the half the frame shares with its predecessor
-    (known before the frame is loaded); a louder second half makes the kernel drop the stage-1 attempt and fold the
-    frame again (csrc/logmel.cuh, "block scale").  Parity must not depend on which way a frame went."""
+    """fp16 build: the per-frame block scale is first guessed from the half the frame shares with its predecessor
+    (known before the frame is loaded); a second half that is louder by a scale step makes the kernel drop the stage-1
+    attempt and fold the frame again (csrc/logmel.cuh, "block scale").  Parity must not depend on which way a frame went."""
     n = 15840 * 24 + 3000
     y = _level_steps(n, levels)
     out, ref = gpu_logmel(y), R.waveform_to_log_mel(y)
