@@ -48,6 +48,9 @@
 #ifndef SEDB_INCR_FRAME
 #define SEDB_INCR_FRAME 0
 #endif
+#ifndef SEDB_ROW128_FOLD
+#define SEDB_ROW128_FOLD 1
+#endif
 #ifndef SEDB_KAHEAD
 #define SEDB_KAHEAD 2
 #endif
@@ -953,12 +956,37 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
 
             // ---------------------------------------------------------------- twiddle, radix-2, stage-2 A operand
             // (the row-128 input Y[n2,128] only needs the fold's partial sums: formed while the last stage-1 MMAs drain)
+#if SEDB_ROW128_FOLD
+            // Y[n2] and Y[128 - n2] meet the same |cos|, |sin| (the frequency index 2 k2 + 1 is odd): the 128-term sums of
+            // the row-128 step become 64-term sums over A[n2] = Y[n2] - Y[128 - n2] (cos part) and B[n2] = Y[n2] + Y[128 - n2]
+            // (sin part); Y[64] only has a sin term, (-1)^k2.  v_s = A[0..63] | B[0..63], red_s[28] = Y[64].
+            if (tid <= 64) {
+                auto ysum = [&](int n2) {
+                    float acc = x128_s[n2];
+#pragma unroll
+                    for (int rr = 0; rr < 16; ++rr) acc += alt_s[rr * 128 + n2];
+                    return acc;                                       // Y[n2,128] (scaled)
+                };
+                const float y0 = ysum(tid);
+                if (tid == 64) {
+                    red_s[28] = y0;
+                } else if (tid == 0) {
+                    v_s[0] = y0;
+                    v_s[64] = 0.f;
+                } else {
+                    const float y1 = ysum(128 - tid);
+                    v_s[tid] = y0 - y1;
+                    v_s[64 + tid] = y0 + y1;
+                }
+            }
+#else
             if (tid < 128) {
                 float acc = x128_s[tid];
 #pragma unroll
                 for (int rr = 0; rr < 16; ++rr) acc += alt_s[rr * 128 + tid];
                 v_s[tid] = acc;                                       // Y[n2,128] (scaled)
             }
+#endif
             mbar_wait(d1_full, attempt & 1);
             ++attempt;
             tc_fence_after();
@@ -1038,6 +1066,16 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 const int part = tid & 7;
                 float ar = 0.f, ai = 0.f;
                 const int mm = 2 * k2 + 1;
+#if SEDB_ROW128_FOLD
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int n2 = part + 8 * i;                      // interleaved: table reads spread over banks
+                    const float2 w = cs_s[(n2 * mm) & 255];
+                    ar = fmaf(v_s[n2], w.x, ar);
+                    ai = fmaf(v_s[64 + n2], w.y, ai);
+                }
+                if (part == 0) ai += (k2 & 1) ? red_s[28] : -red_s[28];   // - i Y[64] sin(pi (2 k2 + 1) / 2)
+#else
 #pragma unroll 8
                 for (int i = 0; i < 16; ++i) {
                     const int n2 = part + 8 * i;                      // interleaved: table reads spread over banks
@@ -1046,6 +1084,7 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                     ar = fmaf(v, w.x, ar);
                     ai = fmaf(v, w.y, ai);
                 }
+#endif
 #pragma unroll
                 for (int o = 1; o < 8; o <<= 1) {
                     ar += __shfl_xor_sync(0xffffffffu, ar, o);

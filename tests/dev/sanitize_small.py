@@ -9,6 +9,13 @@ from sed_b200.train import DataParallelTrainer
 from sed_b200.utils.common import WeightedBCE
 y = np.stack([signals.hdr(100000, i) for i in range(2)])
 lm = P.waveform_to_log_mel(torch.from_numpy(y).float().cuda())
+# more frames than SMs (consecutive runs: block scale taken from the previous frame) with level steps (rejected attempts)
+rng = np.random.default_rng(0)
+y2 = rng.standard_normal((64, 15840 * 7 + 100)).astype(np.float32) * 0.1
+for i in range(0, y2.shape[1], 15840):
+    y2[:, i:i + 15840] *= (1e-3, 0.5, 0.05, 1.0, 0.0, 0.2)[(i // 15840) % 6]
+lm2 = P.waveform_to_log_mel(torch.from_numpy(np.clip(y2, -1, 1)).cuda())
+lm3 = P.pcm16_to_log_mel(torch.from_numpy((np.clip(y2[:40], -1, 1) * 32767).astype(np.int16)).cuda())
 m, _ = refmodels.seeded_cnn(refmodels.MAIN_CFG); m = m.cuda()
 p = m.logits(torch.randn(3, 1, 61, 64, device="cuda"))
 m5, _ = refmodels.seeded_m5(); m5 = m5.cuda()
