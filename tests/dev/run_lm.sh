@@ -1,1 +1,1 @@
-python -m pytest tests/test_gpu_cnn.py -q -m gpu 2>&1 | tail -3
+python tests/dev/lm_sustain.py 2>&1 | tail -14
