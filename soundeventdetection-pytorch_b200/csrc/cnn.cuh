@@ -554,6 +554,90 @@ __global__ void __launch_bounds__(256) conv_in2d_kernel(const float* __restrict_
     }
 }
 
+// The same layer with FOUR vertically adjacent output pixels (rows h0..h0+3 of one column) per thread.  The one-pixel
+// kernel issues one broadcast LDS per FMA (288 per pixel: it is bound by the LSU at 92 us per 256 clips); here a tap's
+// eight weights of a channel group come in with two LDS.128 and feed 32 FMAs (packed: 16 issue slots), the 6 x 3 input
+// window is loaded once, and the lanes of a warp are neighbours along W, so every store instruction of a warp writes 512
+// contiguous bytes of a plane row.  Weights in shared memory as [tap][cout].  The arithmetic per output (tap order, fmaf
+// chain, folded BN) is the one-pixel kernel's, so both produce identical planes.
+template <int RAW>
+__global__ void __launch_bounds__(256, 3) conv_in2d_px4_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                            const float* __restrict__ scale,
+                                                            const float* __restrict__ shift, uint8_t* __restrict__ out,
+                                                            int n_img, int H, int W, int cout, int S_out) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    float* w_s = reinterpret_cast<float*>(smem);     // [9][cout]
+    float* sc_s = w_s + cout * 9;
+    float* sh_s = sc_s + cout;
+    for (int i = threadIdx.x; i < cout * 9; i += blockDim.x) w_s[(i % 9) * cout + i / 9] = w[i];
+    if (!RAW)
+        for (int i = threadIdx.x; i < cout; i += blockDim.x) {
+            sc_s[i] = scale[i];
+            sh_s[i] = shift[i];
+        }
+    __syncthreads();
+    const int H4 = (H + 3) / 4;
+    const long long total = static_cast<long long>(n_img) * H4 * W;
+    const int Wp = W + 2;
+    for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+         idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int wq = static_cast<int>(idx % W);
+        const int h0 = static_cast<int>((idx / W) % H4) * 4;
+        const int img = static_cast<int>(idx / (static_cast<long long>(W) * H4));
+        const float* xi = x + static_cast<long long>(img) * H * W;
+        float v[6][3];                                   // input rows h0-1..h0+4, columns wq-1..wq+1 (zero outside the image)
+#pragma unroll
+        for (int rr = 0; rr < 6; ++rr) {
+            const int hh = h0 + rr - 1;
+            const bool row_ok = hh >= 0 && hh < H;
+            const float* xr = xi + static_cast<long long>(hh) * W + wq;
+            v[rr][0] = (row_ok && wq > 0) ? __ldg(xr - 1) : 0.f;
+            v[rr][1] = row_ok ? __ldg(xr) : 0.f;
+            v[rr][2] = (row_ok && wq + 1 < W) ? __ldg(xr + 1) : 0.f;
+        }
+        const long long vout = kConvLead + static_cast<long long>(h0 + 1) * Wp + wq + 1;
+        const long long out_img = static_cast<long long>(img) * (cout / 8);
+        for (int kg = 0; kg < cout / 8; ++kg) {
+            float2 a[4][4];                              // packed fp32: channel pairs (two FMAs per issue slot)
+#pragma unroll
+            for (int px = 0; px < 4; ++px)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[px][i] = f2s(0.f);
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const float4 wa = *reinterpret_cast<const float4*>(w_s + t * cout + kg * 8);
+                const float4 wb = *reinterpret_cast<const float4*>(w_s + t * cout + kg * 8 + 4);
+                const float2 wt[4] = {f2(wa.x, wa.y), f2(wa.z, wa.w), f2(wb.x, wb.y), f2(wb.z, wb.w)};
+#pragma unroll
+                for (int px = 0; px < 4; ++px) {
+                    const float2 vv = f2s(v[px + t / 3][t % 3]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) a[px][i] = f2fma(vv, wt[i], a[px][i]);
+                }
+            }
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+                if (h0 + px >= H) break;
+                float y[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int c = kg * 8 + i;
+                    const float ai = (i & 1) ? a[px][i >> 1].y : a[px][i >> 1].x;
+                    y[i] = RAW ? ai : fmaxf(0.f, fmaf(ai, sc_s[c], sh_s[c]));
+                }
+                const long long pix = (out_img + kg) * S_out + vout + static_cast<long long>(px) * Wp;
+                if (RAW) {
+                    float4* o = reinterpret_cast<float4*>(out + pix * 32);
+                    o[0] = make_float4(y[0], y[1], y[2], y[3]);
+                    o[1] = make_float4(y[4], y[5], y[6], y[7]);
+                } else {
+                    store_h8(out + pix * 16, y);
+                }
+            }
+        }
+    }
+}
+
 // Head of Cnn_AvgPooling (spectogram_models.py:193-205): mean over freq, Linear, sigmoid, x ratio time repeat.
 // One warp per (image, time step).  in: blocked planes of the last block (C, Hf, Wf): SPLIT 0 = fp16 planes
 // (inference), SPLIT 1 = bf16 hi + lo planes (training).  Lane l handles the 8-channel groups l, l + 32, ...

@@ -504,12 +504,17 @@ int sedb_cnn_forward(sedb_cnn_t* m, const float* x_dev, long long n_clips, long 
     const int n_img = static_cast<int>(n_clips);
     {   // block 0 conv1
         const PlaneGeom& g = plan.planes[0];
-        const long long total = static_cast<long long>(n_img) * g.H * g.W;
+        const bool px4 = true;                      // four rows per thread
+        const long long total = static_cast<long long>(n_img) * (px4 ? (g.H + 3) / 4 : g.H) * g.W;
         long long blocks = (total + 255) / 256;
-        if (blocks > 148LL * 16) blocks = 148LL * 16;
+        if (!px4 && blocks > 148LL * 16) blocks = 148LL * 16;     // (px4: one item per thread, no ragged second pass)
         const size_t smem = static_cast<size_t>(g.C) * 11 * sizeof(float);
-        sedb::conv_in2d_kernel<0><<<static_cast<int>(blocks), 256, smem, st>>>(x_dev, m->w_in, m->scale_in, m->shift_in,
-                                                                              ws + g.offset, n_img, g.H, g.W, g.C, g.S);
+        if (px4)
+            sedb::conv_in2d_px4_kernel<0><<<static_cast<int>(blocks), 256, smem, st>>>(
+                x_dev, m->w_in, m->scale_in, m->shift_in, ws + g.offset, n_img, g.H, g.W, g.C, g.S);
+        else
+            sedb::conv_in2d_kernel<0><<<static_cast<int>(blocks), 256, smem, st>>>(
+                x_dev, m->w_in, m->scale_in, m->shift_in, ws + g.offset, n_img, g.H, g.W, g.C, g.S);
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
     }

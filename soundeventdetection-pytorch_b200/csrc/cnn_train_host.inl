@@ -288,12 +288,17 @@ int sedb_cnn_train_forward(sedb_cnn_t* m, float* const* t, int n_tensors, const 
         float* rmean = q[4 + 4 * tl.which];
         float* rvar = q[5 + 4 * tl.which];
         if (l == 0) {
-            const long long total = static_cast<long long>(n_img) * tl.H * tl.W;
+            const bool px4 = true;                  // four rows per thread
+            const long long total = static_cast<long long>(n_img) * (px4 ? (tl.H + 3) / 4 : tl.H) * tl.W;
             long long blocks = (total + 255) / 256;
-            if (blocks > 148LL * 16) blocks = 148LL * 16;
+            if (!px4 && blocks > 148LL * 16) blocks = 148LL * 16;
             const size_t smem = static_cast<size_t>(tl.cout) * 11 * sizeof(float);
-            sedb::conv_in2d_kernel<1><<<static_cast<int>(blocks), 256, smem, st>>>(
-                x_dev, q[0], nullptr, nullptr, ws + tl.Z.offset, n_img, tl.H, tl.W, tl.cout, tl.Z.S);
+            if (px4)
+                sedb::conv_in2d_px4_kernel<1><<<static_cast<int>(blocks), 256, smem, st>>>(
+                    x_dev, q[0], nullptr, nullptr, ws + tl.Z.offset, n_img, tl.H, tl.W, tl.cout, tl.Z.S);
+            else
+                sedb::conv_in2d_kernel<1><<<static_cast<int>(blocks), 256, smem, st>>>(
+                    x_dev, q[0], nullptr, nullptr, ws + tl.Z.offset, n_img, tl.H, tl.W, tl.cout, tl.Z.S);
             g_launches.fetch_add(1);
         } else {
             if (int rc = launch_umma_layer<1>(m->ctx, m->train->wpack_fwd[l - 1], 1, 0, nullptr, nullptr, tl.fwd,
