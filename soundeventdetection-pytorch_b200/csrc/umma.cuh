@@ -61,6 +61,23 @@ __device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parit
         : "memory");
     return ok != 0;
 }
+// What a timed-out wait does.  A printf here is a real call (vprintf): ptxas then treats most registers as clobbered on
+// the path that rejoins the wait's fast exit and re-derives thread ids, window bases and descriptors after EVERY wait
+// (about a dozen instructions, two of them S2R, per fold chunk of the log-mel kernel).  The default is a bare trap;
+// -DSEDB_MBAR_DEBUG=1 brings the message back.
+#ifndef SEDB_MBAR_DEBUG
+#define SEDB_MBAR_DEBUG 0
+#endif
+__device__ __forceinline__ void mbar_timeout(uint64_t* bar, uint32_t parity) {
+#if SEDB_MBAR_DEBUG
+    printf("sedb: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
+#else
+    (void)bar;
+    (void)parity;
+#endif
+    __trap();
+}
+
 // Bounded wait: a protocol bug must not hang the GPU box.  On timeout (~seconds) the kernel traps, which surfaces
 // as a CUDA launch failure on the host instead of a wedged device.  The timeout clock is only consulted every 256
 // failed (sleeping) probes so that waiting warps do not steal issue slots from working ones.
@@ -76,9 +93,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
             else if (now - t0 > 6000000000LL) {
-                printf("sedb: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
-                       smem_u32(bar), parity);
-                __trap();
+                mbar_timeout(bar, parity);
             }
         }
     }
@@ -110,9 +125,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
             const long long now = clock64();
             if (t0 == 0) t0 = now;
             else if (now - t0 > 6000000000LL) {
-                printf("sedb: mbarrier timeout block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x,
-                       smem_u32(bar), parity);
-                __trap();
+                mbar_timeout(bar, parity);
             }
         }
     }

@@ -1,3 +1,4 @@
-ncu --metrics gpu__time_duration.sum --clock-control none -c 30 --csv --log-file gpurun_out/cnn_launches.csv python tests/dev/cnn_once.py 256 > /dev/null 2>&1
-grep "conv_in2d" gpurun_out/cnn_launches.csv | cut -d, -f5,15- | head -3
-timeout 300 python tests/dev/fixed_cost.py 2>&1 | grep -E "^256|^128 |^16 " | cut -c1-60
+timeout 300 python tests/dev/lm_time.py 256 2>&1 | tail -1
+sleep 2
+SEDB_LIB_PATH=$PWD/tests/dev/lib_z23.so timeout 300 python tests/dev/lm_time.py 256 2>&1 | tail -1
+timeout 1500 python -m pytest tests -q -m gpu 2>&1 | tail -3
