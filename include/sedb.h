@@ -90,6 +90,25 @@ int sedb_power_mel_db_f32(sedb_ctx_t* ctx, const float* spec_dev, long long rows
 int sedb_logmel_host_f32(sedb_ctx_t* ctx, const float* wave_host, long long n_clips, long long n_samples,
                          long long wave_stride, const float* norm_host, float* out_host);
 
+/* ---- sample-rate conversion in front of the path ---------------------------------------------------
+ * Replaces the resampling branch of read_multichannel_audio (dataset/dataset_utils.py:77-84:
+ * `librosa.resample(x, orig_sr=fs, target_sr=target_fs)` per channel) for files that are not at the
+ * working rate.  Band-limited interpolation with a Kaiser-windowed sinc in exact polyphase form, resampy's
+ * `kaiser_best` design (64 zero crossings, roll-off 0.9475937, beta 14.7697: librosa's default before
+ * 0.10; from 0.10 on the default is `soxr_hq`, which is not reproduced).  The reference pins no librosa
+ * version, so parity for this row is unpinned; the oracle (oracle/resample_ref.py) is checked against
+ * torchaudio's sinc_interp_kaiser with the same parameters.
+ * in: [n_clips, in_stride] float32 device, n_in valid samples per clip; out: [n_clips, out_stride] with
+ * sedb_resample_num_samples(n_in, sr_in, sr_out) = ceil(n_in * sr_out / sr_in) samples per clip.  The
+ * first call for a rate pair builds and uploads its filter table (allocates and synchronises: do it
+ * outside graph capture).  Rates that reduce to more than 4096 : 4096 are refused. */
+long long sedb_resample_num_samples(long long n_in, int sr_in, int sr_out);
+/* The filter table the converter uses for a rate pair, [taps][phases] float32 (host; no GPU needed): tap k of
+ * phase p weighs x[i * Lo + k - width] in y[i * Ln + p].  out_host may be null to query the sizes. */
+int sedb_resample_filters(int sr_in, int sr_out, float* out_host, int* width, int* taps, int* phases);
+int sedb_resample_f32(sedb_ctx_t* ctx, const float* in_dev, long long n_clips, long long n_in, long long in_stride,
+                      int sr_in, int sr_out, float* out_dev, long long out_stride, void* stream);
+
 /* ---- 16-bit PCM input: read_multichannel_audio's channel handling fused into the loader -------------
  * Replaces dataset/dataset_utils.py:63-74 (soundfile.read of a PCM_16 file = int16 / 32768, then
  * `.mean(1)` because common_config.audio_channels == 1) followed by the fused log-mel above.

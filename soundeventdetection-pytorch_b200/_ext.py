@@ -32,6 +32,10 @@ _SIGNATURES = {
     "sedb_power_mel_db_f32": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_ll, c_float_p, c_float_p,
                                              ctypes.c_void_p]),
     "sedb_logmel_host_f32": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_ll, c_ll, c_ll, c_float_p, c_float_p]),
+    "sedb_resample_num_samples": (c_ll, [c_ll, ctypes.c_int, ctypes.c_int]),
+    "sedb_resample_filters": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_int)] * 3),
+    "sedb_resample_f32": (ctypes.c_int, [ctypes.c_void_p, c_float_p, c_ll, c_ll, c_ll, ctypes.c_int, ctypes.c_int,
+                                         c_float_p, c_ll, ctypes.c_void_p]),
     "sedb_logmel_pcm16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_ll, c_ll, c_ll, ctypes.c_int, c_float_p,
                                          c_float_p, ctypes.c_void_p]),
     "sedb_logmel_host_pcm16": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, c_ll, c_ll, c_ll, ctypes.c_int,

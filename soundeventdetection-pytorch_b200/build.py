@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsedb.so")
 SOURCES = ["sedb.cu"]
-HEADERS = ["umma.cuh", "logmel.cuh", "probe.cuh", "cnn.cuh", "conv_issue.cuh", "cnn_host.inl", "cnn_train.cuh", "cnn_train_host.inl", "host_tables.h",
+HEADERS = ["umma.cuh", "logmel.cuh", "resample.cuh", "probe.cuh", "cnn.cuh", "conv_issue.cuh", "cnn_host.inl", "cnn_train.cuh", "cnn_train_host.inl", "host_tables.h",
            os.path.join("..", "..", "include", "sedb.h")]
 
 

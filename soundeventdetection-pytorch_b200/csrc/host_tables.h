@@ -112,6 +112,42 @@ inline std::vector<float> make_hann_factors(int win, int n_fft) {
     return t;
 }
 
+// ---- polyphase filters of the sample-rate converter (csrc/resample.cuh) ---------------------------------
+// Kaiser-windowed sinc with resampy's `kaiser_best` design (the default of librosa.resample before librosa 0.10):
+// 64 zero crossings, roll-off 0.9475937167399596, beta 14.769656459379492, in exact polyphase form for the reduced
+// rates lo / ln.  Returns the table transposed, [taps][ln] float32 (taps = 2 width + lo), computed in float64.
+constexpr int kResampleZeros = 64;
+constexpr double kResampleRolloff = 0.9475937167399596;
+constexpr double kResampleBeta = 14.769656459379492;
+inline double bessel_i0(double x) {                  // power series; converges fast for x <= ~15
+    double sum = 1.0, term = 1.0;
+    const double q = 0.25 * x * x;
+    for (int k = 1; k < 200; ++k) {
+        term *= q / (static_cast<double>(k) * k);
+        sum += term;
+        if (term < 1e-18 * sum) break;
+    }
+    return sum;
+}
+inline std::vector<float> make_resample_filters(int lo, int ln, int& width, int& taps) {
+    const double base = static_cast<double>(lo < ln ? lo : ln) * kResampleRolloff;
+    width = static_cast<int>(std::ceil(kResampleZeros * static_cast<double>(lo) / base));
+    taps = 2 * width + lo;
+    std::vector<float> h(static_cast<size_t>(taps) * ln);
+    const double i0b = bessel_i0(kResampleBeta);
+    for (int p = 0; p < ln; ++p)
+        for (int k = 0; k < taps; ++k) {
+            double t = (static_cast<double>(k - width) / lo - static_cast<double>(p) / ln) * base;
+            if (t < -kResampleZeros) t = -kResampleZeros;
+            if (t > kResampleZeros) t = kResampleZeros;
+            const double r = t / kResampleZeros;
+            const double win = bessel_i0(kResampleBeta * std::sqrt(std::fmax(0.0, 1.0 - r * r))) / i0b;
+            const double sinc = (t == 0.0) ? 1.0 : std::sin(kPi * t) / (kPi * t);
+            h[static_cast<size_t>(k) * ln + p] = static_cast<float>(sinc * win * (base / lo));
+        }
+    return h;
+}
+
 // ---- librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax, htk=False, norm='slaney') --------------------
 inline double hz_to_mel(double f) {
     const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp;

@@ -17,6 +17,7 @@
 #include "../../include/sedb.h"
 #include "host_tables.h"
 #include "logmel.cuh"
+#include "resample.cuh"
 #include "probe.cuh"
 #include "cnn.cuh"
 #include "cnn_train.cuh"
@@ -67,6 +68,12 @@ struct sedb_ctx {
     size_t d_ws_bytes[2] = {0, 0};        // (the activation planes keep their zero padding per geometry, see ws_zero_kernel)
     float* d_probs = nullptr;
     size_t d_probs_elems = 0;
+    // polyphase filter tables of the sample-rate converter, one per reduced rate pair (built on first use)
+    struct ResampleTable {
+        int lo = 0, ln = 0, width = 0, taps = 0;
+        float* h = nullptr;
+    };
+    std::vector<ResampleTable> resample_tables;
 };
 
 #include "cnn_host.inl"
@@ -177,6 +184,7 @@ int sedb_destroy(sedb_ctx_t* c) {
     cudaFree(c->d_ws[0]);
     cudaFree(c->d_ws[1]);
     cudaFree(c->d_probs);
+    for (auto& t : c->resample_tables) cudaFree(t.h);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
     if (c->s_comp) cudaStreamDestroy(c->s_comp);
     delete c;
@@ -231,6 +239,105 @@ static int launch_logmel(sedb_ctx_t* c, int mode, const void* wave, long long n_
         sedb::logmel_fused_kernel<1, 0><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
     else
         return fail("the complex STFT output takes float32 input");
+    g_launches.fetch_add(1);
+    CUDA_TRY(cudaGetLastError());
+    return 0;
+}
+
+static long long gcd_ll(long long a, long long b) {
+    while (b) {
+        const long long t = a % b;
+        a = b;
+        b = t;
+    }
+    return a;
+}
+
+long long sedb_resample_num_samples(long long n_in, int sr_in, int sr_out) {
+    if (n_in < 0 || sr_in <= 0 || sr_out <= 0) return -1;
+    const long long g = gcd_ll(sr_in, sr_out), lo = sr_in / g, ln = sr_out / g;
+    return (n_in * ln + lo - 1) / lo;                       // librosa.resample: ceil(n * target_sr / orig_sr)
+}
+
+int sedb_resample_filters(int sr_in, int sr_out, float* out_host, int* width, int* taps, int* phases) {
+    if (sr_in <= 0 || sr_out <= 0) return fail("sample rates must be positive");
+    const long long g = gcd_ll(sr_in, sr_out);
+    const int lo = static_cast<int>(sr_in / g), ln = static_cast<int>(sr_out / g);
+    if (lo > 4096 || ln > 4096) return fail("rates %d -> %d reduce to %d / %d", sr_in, sr_out, lo, ln);
+    int w = 0, t = 0;
+    std::vector<float> h = sedb_host::make_resample_filters(lo, ln, w, t);
+    if (width) *width = w;
+    if (taps) *taps = t;
+    if (phases) *phases = ln;
+    if (out_host) std::memcpy(out_host, h.data(), h.size() * sizeof(float));
+    return 0;
+}
+
+int sedb_resample_f32(sedb_ctx_t* c, const float* in_dev, long long n_clips, long long n_in, long long in_stride,
+                      int sr_in, int sr_out, float* out_dev, long long out_stride, void* stream) {
+    if (!c) return fail("null context");
+    if (n_clips < 0 || n_in < 0) return fail("negative size");
+    if (sr_in <= 0 || sr_out <= 0) return fail("sample rates must be positive");
+    if (n_clips == 0 || n_in == 0) return 0;
+    if (!in_dev || !out_dev) return fail("null buffer");
+    if (n_clips > 65535) return fail("n_clips=%lld: at most 65535 clips per call", n_clips);
+    const long long g = gcd_ll(sr_in, sr_out);
+    const int lo = static_cast<int>(sr_in / g), ln = static_cast<int>(sr_out / g);
+    const long long n_out = sedb_resample_num_samples(n_in, sr_in, sr_out);
+    if (n_in > 2000000000LL || n_out > 2000000000LL) return fail("clip too long");
+    if (in_stride < n_in || out_stride < n_out) return fail("stride shorter than the clip");
+    if (lo > 4096 || ln > 4096)
+        return fail("rates %d -> %d reduce to %d / %d: more than 4096 phases or samples per block", sr_in, sr_out, lo, ln);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (lo == ln) {
+        CUDA_TRY(cudaMemcpy2DAsync(out_dev, out_stride * sizeof(float), in_dev, in_stride * sizeof(float),
+                                   n_in * sizeof(float), n_clips, cudaMemcpyDeviceToDevice, st));
+        return 0;
+    }
+    const sedb_ctx::ResampleTable* tab = nullptr;
+    for (const auto& t : c->resample_tables)
+        if (t.lo == lo && t.ln == ln) tab = &t;
+    if (!tab) {                                              // first use of this rate pair (allocates: not under graph capture)
+        sedb_ctx::ResampleTable t;
+        t.lo = lo;
+        t.ln = ln;
+        std::vector<float> h = sedb_host::make_resample_filters(lo, ln, t.width, t.taps);
+        CUDA_TRY(cudaMalloc(&t.h, h.size() * sizeof(float)));
+        cudaError_t e = cudaMemcpy(t.h, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            cudaFree(t.h);
+            return fail("cudaMemcpy(resample filters): %s", cudaGetErrorString(e));
+        }
+        c->resample_tables.push_back(t);
+        tab = &c->resample_tables.back();
+    }
+    sedb::ResampleParams p;
+    p.x = in_dev;
+    p.y = out_dev;
+    p.h = tab->h;
+    p.in_stride = in_stride;
+    p.out_stride = out_stride;
+    p.n_in = static_cast<int>(n_in);
+    p.n_out = static_cast<int>(n_out);
+    p.lo = lo;
+    p.ln = ln;
+    p.width = tab->width;
+    p.taps = tab->taps;
+    // tile: about 1024 (phase, block-group) items, input span at most 12288 floats of shared memory
+    const int per = sedb::kResampleBlocksPerThread;
+    int nb = per * ((1024 + ln - 1) / ln);
+    const int nb_cap = ((12288 - p.taps) / lo + 1) / per * per;
+    if (nb > nb_cap) nb = nb_cap;
+    if (nb < per) nb = per;
+    p.nb = nb;
+    const size_t smem = (static_cast<size_t>(nb - 1) * lo + p.taps) * sizeof(float);
+    if (smem > 200 * 1024) return fail("rates %d -> %d: filter span does not fit shared memory", sr_in, sr_out);
+    if (smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(sedb::resample_fir_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      static_cast<int>(smem)));
+    const long long n_blocks = (n_out + ln - 1) / ln;
+    const dim3 grid(static_cast<unsigned>((n_blocks + nb - 1) / nb), static_cast<unsigned>(n_clips));
+    sedb::resample_fir_kernel<<<grid, sedb::kResampleThreads, smem, st>>>(p);
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return 0;

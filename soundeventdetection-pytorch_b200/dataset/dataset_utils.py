@@ -4,8 +4,10 @@
 when it is installed and falls back to the standard library's ``wave`` module for 16-bit PCM WAV files (the format of
 both datasets the reference trains on).  ``read_wav_pcm16`` returns the samples as stored -- int16, interleaved --
 for :func:`sed_b200.dataset.spectogram.preprocess.pcm16_to_log_mel`, which fuses the ``/ 32768`` scaling and the channel
-mean into the log-mel kernel's loader.  Resampling (``librosa.resample``, dataset_utils.py:77-84) is not provided:
-files must already be at ``target_fs``.
+mean into the log-mel kernel's loader.  Files at another rate are converted on the GPU by :func:`resample`
+(``sedb_resample_f32``: Kaiser-windowed sinc, resampy's ``kaiser_best`` design), the counterpart of the reference's
+``librosa.resample`` call (dataset_utils.py:77-84; parity unpinned: the reference pins no librosa version and newer
+versions default to ``soxr_hq``).
 """
 import wave
 
@@ -40,6 +42,37 @@ def apply_channel_policy(multichannel_audio):
     return a
 
 
+def resample(audio, orig_sr, target_sr):
+    """``librosa.resample(audio, orig_sr=..., target_sr=...)`` for the last axis of ``audio`` on the GPU: NumPy in ->
+    NumPy out (the input's floating dtype), CUDA tensor in -> float32 CUDA tensor out.  The arithmetic is float32."""
+    import torch
+    from .. import _ext
+    is_np = not isinstance(audio, torch.Tensor)
+    x = torch.as_tensor(np.ascontiguousarray(audio) if is_np else audio)
+    if not x.is_floating_point():
+        raise TypeError("resample expects floating-point samples")
+    if int(orig_sr) != orig_sr or int(target_sr) != target_sr or orig_sr <= 0 or target_sr <= 0:
+        raise ValueError("sample rates must be positive integers")
+    out_dtype = x.dtype
+    lead = x.shape[:-1]
+    w = x.reshape(-1, x.shape[-1]).to(device="cuda" if not x.is_cuda else x.device, dtype=torch.float32).contiguous()
+    lib = _ext.load()
+    n_out = int(lib.sedb_resample_num_samples(w.shape[1], int(orig_sr), int(target_sr)))
+    out = torch.empty((w.shape[0], n_out), dtype=torch.float32, device=w.device)
+    if w.numel():
+        with torch.cuda.device(w.device):
+            _ext.check(lib.sedb_resample_f32(_ext.context(), w.data_ptr(), w.shape[0], w.shape[1], w.stride(0),
+                                             int(orig_sr), int(target_sr), out.data_ptr(), out.stride(0),
+                                             _ext.stream_ptr()))
+    out = out.reshape(*lead, n_out)
+    return out.cpu().numpy().astype(_np_dtype(out_dtype)) if is_np else out
+
+
+def _np_dtype(torch_dtype):
+    import torch
+    return {torch.float64: np.float64, torch.float32: np.float32, torch.float16: np.float16}.get(torch_dtype, np.float32)
+
+
 def read_multichannel_audio(audio_path, target_fs=None):
     """Reference signature and result: float64 ``(samples, audio_channels)`` at ``target_fs``."""
     try:
@@ -50,6 +83,6 @@ def read_multichannel_audio(audio_path, target_fs=None):
         audio = pcm.astype(np.float64) / 32768.0               # soundfile's scaling of PCM_16
     audio = apply_channel_policy(audio)
     if target_fs is not None and sample_rate != target_fs:
-        raise RuntimeError(f"{audio_path}: sample rate {sample_rate} != {target_fs}; resample the file first "
-                           "(librosa.resample is outside this package)")
+        # dataset_utils.py:77-84: every channel resampled on its own
+        audio = np.ascontiguousarray(resample(np.ascontiguousarray(audio.T), sample_rate, target_fs).T)
     return audio

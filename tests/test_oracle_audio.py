@@ -75,3 +75,54 @@ def test_wav_reader_rejects_other_sample_widths(tmp_path):
         w.writeframes(bytes(100))
     with pytest.raises(ValueError):
         DU.read_wav_pcm16(str(path))
+
+
+# ---- resampling (reference dataset_utils.py:77-84) -----------------------------------------------------------------
+RATE_PAIRS = [(44100, 48000), (32000, 48000), (16000, 48000), (96000, 48000), (22050, 48000), (8000, 48000),
+              (48000, 16000)]
+
+
+@pytest.mark.parametrize("orig,new", RATE_PAIRS)
+def test_resample_oracle_is_pinned_by_torchaudio(orig, new):
+    """The oracle restates a Kaiser-windowed sinc interpolation with resampy's kaiser_best parameters; the independent
+    implementation installed here is torchaudio's sinc_interp_kaiser with the same three parameters."""
+    torch = pytest.importorskip("torch")
+    F = pytest.importorskip("torchaudio.functional")
+    from oracle import resample_ref as R
+    x = np.random.default_rng(orig + new).standard_normal(20011)
+    y = R.resample(x, orig, new)
+    t = F.resample(torch.from_numpy(x), orig, new, lowpass_filter_width=R.LOWPASS_FILTER_WIDTH, rolloff=R.ROLLOFF,
+                   resampling_method="sinc_interp_kaiser", beta=R.KAISER_BETA).numpy()
+    assert y.shape == t.shape == (-(-20011 * new // orig),)            # librosa: ceil(n * target_sr / orig_sr)
+    assert np.abs(y - t).max() < 5e-7
+
+
+def test_resample_oracle_properties():
+    from oracle import resample_ref as R
+    x = np.random.default_rng(1).standard_normal(1000)
+    np.testing.assert_array_equal(R.resample(x, 48000, 48000), x)
+    # a tone well below both Nyquist rates is reproduced at the new rate (away from the clip's ends)
+    n, f = 44100, 1000.0
+    y = R.resample(np.sin(2 * np.pi * f * np.arange(n) / 44100), 44100, 48000)
+    ref = np.sin(2 * np.pi * f * np.arange(y.size) / 48000)
+    assert y.size == 48000 and np.abs(y - ref)[200:-200].max() < 1e-4
+    # unit DC gain of every phase
+    h, _ = R.polyphase_filters(44100, 48000)
+    assert np.abs(h.sum(1) - 1.0).max() < 1e-4
+
+
+@pytest.mark.parametrize("orig,new", RATE_PAIRS)
+def test_library_filter_table_matches_oracle(orig, new):
+    """host_tables.h: make_resample_filters (float64 on the host, stored [tap][phase] float32) == the oracle's filters."""
+    import ctypes
+    from sed_b200 import _ext
+    from oracle import resample_ref as R
+    lib = _ext.load()
+    w, t, p = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    _ext.check(lib.sedb_resample_filters(orig, new, None, ctypes.byref(w), ctypes.byref(t), ctypes.byref(p)))
+    h, width = R.polyphase_filters(orig, new)
+    assert (p.value, t.value, w.value) == (h.shape[0], h.shape[1], width)
+    tab = np.empty((t.value, p.value), dtype=np.float32)
+    _ext.check(lib.sedb_resample_filters(orig, new, ctypes.c_void_p(tab.ctypes.data), None, None, None))
+    assert np.abs(tab.T.astype(np.float64) - h).max() < 1e-7
+    assert lib.sedb_resample_num_samples(20011, orig, new) == R.num_samples(20011, orig, new)
