@@ -115,6 +115,9 @@ __device__ __forceinline__ void load_h8(const uint8_t* ptr, float* y) {
     }
 }
 
+#ifndef SEDB_CONV_PDL
+#define SEDB_CONV_PDL 1
+#endif
 // shared memory: [patch | weight ring | pooling stage | scale/shift | barriers | tmem ptr].  The accumulators are double
 // buffered in TMEM (columns 0..255 / 256..511 for even / odd work items) so that the patch load and the MMAs of item
 // t+1 overlap the epilogue of item t.
@@ -168,6 +171,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr_s;
+    if (AMODE == 0 && SEDB_CONV_PDL) {
+        // set-up done: let the next layer's CTAs be placed as SMs free up, then wait for the previous layer's results
+        // (and for its reads of the planes this layer overwrites).  Both are no-ops for a launch without the attribute.
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
 
     const int nsplit = p.n_ntiles * p.n_nsub;
     const int items_total = p.n_img * p.n_bands * nsplit;
@@ -646,6 +655,7 @@ __global__ void __launch_bounds__(256) head2d_kernel(const uint8_t* __restrict__
                                                      const float* __restrict__ fc_b, float* __restrict__ logits,
                                                      float* __restrict__ probs, int n_img, int C, int Hf, int Wf,
                                                      int S_in, int classes, int ratio) {
+    if (SPLIT == 0) asm volatile("griddepcontrol.wait;" ::: "memory");   // inference: launched programmatically behind the last conv
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp_global >= n_img * Hf) return;
@@ -878,6 +888,7 @@ __global__ void pack_front_weight_kernel(const float* __restrict__ w, uint8_t* _
 __global__ void __launch_bounds__(256) head1d_kernel(const uint8_t* __restrict__ in, const float* __restrict__ fc_w,
                                                      const float* __restrict__ fc_b, float* __restrict__ logits,
                                                      int n, int C, int Lf, int S_in, int classes) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");                   // launched programmatically behind the last conv
     const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wg >= n) return;

@@ -196,6 +196,24 @@ void free_layer_params(UmmaLayer& L) {
     L.scale = L.shift = nullptr;
 }
 
+// Launch with programmatic stream serialization: the kernel may be placed while its predecessor in the stream is still
+// running (after the predecessor's `griddepcontrol.launch_dependents`); it must execute `griddepcontrol.wait` before it
+// touches global memory.
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 template <int AMODE>
 int launch_umma_layer(const sedb_ctx* c, const uint8_t* wpack, int w_nrep, size_t w_rep_bytes, const float* scale,
                       const float* shift, sedb::ConvParams p, const uint8_t* in, uint8_t* out, int n_img, int S_in,
@@ -216,7 +234,14 @@ int launch_umma_layer(const sedb_ctx* c, const uint8_t* wpack, int w_nrep, size_
     const int grid = static_cast<int>(items < c->num_sms ? items : c->num_sms);
     const size_t smem = conv_smem_bytes(p);
     if (smem > 227 * 1024) return fail("conv layer needs %zu bytes of shared memory", smem);
-    sedb::conv_umma_kernel<AMODE><<<grid, sedb::kConvThreads, smem, st>>>(p);
+    if (AMODE == 0 && SEDB_CONV_PDL) {
+        // Programmatic dependent launch between the inference layers: the kernel's set-up (barriers, TMEM allocation,
+        // folded-BN constants) runs on every SM the previous layer has already left; `griddepcontrol.wait` in the kernel
+        // holds all global-memory traffic until the previous grid has completed and flushed.
+        CUDA_TRY(launch_pdl(sedb::conv_umma_kernel<AMODE>, dim3(static_cast<unsigned>(grid)), dim3(sedb::kConvThreads), smem, st, p));
+    } else {
+        sedb::conv_umma_kernel<AMODE><<<grid, sedb::kConvThreads, smem, st>>>(p);
+    }
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -528,8 +553,10 @@ int sedb_cnn_forward(sedb_cnn_t* m, const float* x_dev, long long n_clips, long 
         const PlaneGeom& g = plan.planes.back();
         const long long warps = static_cast<long long>(n_img) * plan.Hf;
         const int blocks = static_cast<int>((warps * 32 + 255) / 256);
-        sedb::head2d_kernel<0><<<blocks, 256, 0, st>>>(ws + g.offset, m->fc_w, m->fc_b, logits_dev, probs_dev, n_img, g.C,
-                                                      plan.Hf, plan.Wf, g.S, m->classes, m->ratio);
+        CUDA_TRY(launch_pdl(sedb::head2d_kernel<0>, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st,
+                            static_cast<const uint8_t*>(ws + g.offset), static_cast<const float*>(m->fc_w),
+                            static_cast<const float*>(m->fc_b), logits_dev, probs_dev, n_img, g.C, plan.Hf, plan.Wf, g.S,
+                            m->classes, m->ratio));
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
     }
@@ -762,8 +789,9 @@ int sedb_m5_forward(sedb_m5_t* m, const float* x_dev, long long n_frames, float*
     {
         const PlaneGeom& g = plan.planes[8];
         const int blocks = (n * 32 + 255) / 256;
-        sedb::head1d_kernel<<<blocks, 256, 0, st>>>(ws + g.offset, m->fc_w, m->fc_b, logits_dev, n, g.C, plan.Lf, g.S,
-                                                   m->classes);
+        CUDA_TRY(launch_pdl(sedb::head1d_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, st,
+                            static_cast<const uint8_t*>(ws + g.offset), static_cast<const float*>(m->fc_w),
+                            static_cast<const float*>(m->fc_b), logits_dev, n, g.C, plan.Lf, g.S, m->classes));
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
     }
