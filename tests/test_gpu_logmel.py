@@ -182,7 +182,11 @@ def test_dynamic_range_contract_pcm16_tone_with_dither():
           f"{inside:.2e} dB, outside {outside:.2e} dB (reads high by at most {over:.2e} dB)")
     assert inside < TOL_DB
     assert depth > DYN_RANGE_DB - 5.0                        # the case really reaches the edge of the window
-    assert outside < 1.0                                     # measured ~0.1 dB on B200 (fp16 split)
+    if DYN_RANGE_DB >= 100.0:
+        assert outside < 1.0                                 # measured ~0.2 dB on B200 (fp16 split)
+    else:                                                    # bf16 build: 45 dB of bins lie outside its 75 dB window; the
+        top = ref.max(axis=-1, keepdims=True)                # contract there is only "stays below the window" (1.9 dB measured)
+        assert np.all((out < top - DYN_RANGE_DB + 3.0)[ref <= top - DYN_RANGE_DB])
     # the same samples through the 16-bit PCM entry point are the same features
     from sed_b200.dataset.spectogram.preprocess import pcm16_to_log_mel
     out16 = pcm16_to_log_mel(torch.from_numpy(pcm[None]).cuda()).cpu().numpy()[0]
