@@ -171,12 +171,9 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_umma_kernel(const ConvPa
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr_s;
-    if (AMODE == 0 && SEDB_CONV_PDL) {
-        // set-up done: let the next layer's CTAs be placed as SMs free up, then wait for the previous layer's results
-        // (and for its reads of the planes this layer overwrites).  Both are no-ops for a launch without the attribute.
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-    }
+    // set-up done: let the next kernel's CTAs be placed as SMs free up, then wait for the previous kernel's results (and
+    // for its reads of the planes this layer overwrites).  Both are no-ops for a launch without the attribute.
+    if (SEDB_CONV_PDL) pdl_entry();
 
     const int nsplit = p.n_ntiles * p.n_nsub;
     const int items_total = p.n_img * p.n_bands * nsplit;
@@ -513,6 +510,7 @@ __global__ void __launch_bounds__(256) conv_in2d_kernel(const float* __restrict_
                                                         const float* __restrict__ scale, const float* __restrict__ shift,
                                                         uint8_t* __restrict__ out, int n_img, int H, int W, int cout,
                                                         int S_out) {
+    pdl_entry();
     extern __shared__ __align__(128) uint8_t smem[];
     float* w_s = reinterpret_cast<float*>(smem);     // [cout][9]
     float* sc_s = w_s + cout * 9;
@@ -574,6 +572,7 @@ __global__ void __launch_bounds__(256, 3) conv_in2d_px4_kernel(const float* __re
                                                             const float* __restrict__ scale,
                                                             const float* __restrict__ shift, uint8_t* __restrict__ out,
                                                             int n_img, int H, int W, int cout, int S_out) {
+    pdl_entry();
     extern __shared__ __align__(128) uint8_t smem[];
     float* w_s = reinterpret_cast<float*>(smem);     // [9][cout]
     float* sc_s = w_s + cout * 9;
@@ -655,7 +654,7 @@ __global__ void __launch_bounds__(256) head2d_kernel(const uint8_t* __restrict__
                                                      const float* __restrict__ fc_b, float* __restrict__ logits,
                                                      float* __restrict__ probs, int n_img, int C, int Hf, int Wf,
                                                      int S_in, int classes, int ratio) {
-    if (SPLIT == 0) asm volatile("griddepcontrol.wait;" ::: "memory");   // inference: launched programmatically behind the last conv
+    pdl_entry();
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp_global >= n_img * Hf) return;
@@ -888,7 +887,7 @@ __global__ void pack_front_weight_kernel(const float* __restrict__ w, uint8_t* _
 __global__ void __launch_bounds__(256) head1d_kernel(const uint8_t* __restrict__ in, const float* __restrict__ fc_w,
                                                      const float* __restrict__ fc_b, float* __restrict__ logits,
                                                      int n, int C, int Lf, int S_in, int classes) {
-    asm volatile("griddepcontrol.wait;" ::: "memory");                   // launched programmatically behind the last conv
+    pdl_entry();
     const int wg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wg >= n) return;

@@ -234,8 +234,8 @@ int launch_umma_layer(const sedb_ctx* c, const uint8_t* wpack, int w_nrep, size_
     const int grid = static_cast<int>(items < c->num_sms ? items : c->num_sms);
     const size_t smem = conv_smem_bytes(p);
     if (smem > 227 * 1024) return fail("conv layer needs %zu bytes of shared memory", smem);
-    if (AMODE == 0 && SEDB_CONV_PDL) {
-        // Programmatic dependent launch between the inference layers: the kernel's set-up (barriers, TMEM allocation,
+    if (SEDB_CONV_PDL) {
+        // Programmatic dependent launch between the layers (inference and training): the kernel's set-up (barriers, TMEM allocation,
         // folded-BN constants) runs on every SM the previous layer has already left; `griddepcontrol.wait` in the kernel
         // holds all global-memory traffic until the previous grid has completed and flushed.
         CUDA_TRY(launch_pdl(sedb::conv_umma_kernel<AMODE>, dim3(static_cast<unsigned>(grid)), dim3(sedb::kConvThreads), smem, st, p));

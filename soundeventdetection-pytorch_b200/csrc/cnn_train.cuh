@@ -51,6 +51,7 @@ __device__ __forceinline__ void bn_channel_consts(const double* __restrict__ sum
 // grid = (chunks, C/8): block (x, kg) walks its share of the (image, pixel) pairs of group kg.
 __global__ void __launch_bounds__(256) bn_stats_kernel(const float* __restrict__ z, int n_img, int C, int H, int W, int S,
                                                        double* __restrict__ sums) {
+    pdl_entry();
     const int kg = blockIdx.y, nkg = C / 8, Wp = W + 2;
     const int total = n_img * H * W;                 // < 2^31 (checked by the host)
     float s[8], ss[8];
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(256) bn_apply_kernel(const float* __restrict__
                                                        float* __restrict__ running_mean, float* __restrict__ running_var,
                                                        float momentum, int n_img, int C, int H, int W, int S_z, int pool,
                                                        int S_out, uint8_t* __restrict__ out) {
+    pdl_entry();
     extern __shared__ float bn_s[];
     float* a_s = bn_s;
     float* b_s = bn_s + C;
@@ -156,6 +158,7 @@ __global__ void __launch_bounds__(1024) bce_logits_kernel(const float* __restric
                                                           int B, int F_out, int F_tgt, int K, float pos_weight,
                                                           float grad_scale, float* __restrict__ loss,
                                                           float* __restrict__ dlogits) {
+    pdl_entry();
     const int N = min(F_out, F_tgt);
     const long long count = static_cast<long long>(B) * N * K;
     const float inv = 1.0f / static_cast<float>(count);
@@ -198,6 +201,7 @@ __global__ void __launch_bounds__(256) head2d_bwd_kernel(const uint8_t* __restri
                                                          const float* __restrict__ dlogits, float* __restrict__ d_fc_w,
                                                          float* __restrict__ d_fc_b, float* __restrict__ g_out, int n_img,
                                                          int C, int Hf, int Wf, int S_in, int S_g, int classes, int ratio) {
+    pdl_entry();
     const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp_global >= n_img * Hf) return;
@@ -271,6 +275,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const float* __restr
                                                             const double* __restrict__ sums, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, int n_img, int C, int H, int W,
                                                             int S_z, int pool, int S_g, double* __restrict__ bsum) {
+    pdl_entry();
     __shared__ float a_s[8], b_s[8], mean_s[8], rstd_s[8];
     __shared__ double red[8][16];
     const int kg = blockIdx.y, nkg = C / 8, Wp = W + 2;
@@ -336,6 +341,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const float* __restri
                                                            int S_dz, uint8_t* __restrict__ dz, float* __restrict__ d_gamma,
                                                            float* __restrict__ d_beta, const float* __restrict__ x_in,
                                                            float* __restrict__ d_w) {
+    pdl_entry();
     __shared__ float a_s[8], b_s[8], mean_s[8], rstd_s[8], m1_s[8], m2_s[8];
     __shared__ float wred[8][72];
     const int kg = blockIdx.y, nkg = C / 8, Wp = W + 2;
@@ -460,6 +466,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_umma_kernel(const WgradPa
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_ptr_s;
+    pdl_entry();                                       // set-up done (barriers, TMEM); see umma.cuh
     const int items_total = p.n_img * p.n_bands;
     const int n_items = (pc < items_total) ? (items_total - pc + p.n_pc - 1) / p.n_pc : 0;
     // stage layout: dZ [half][mkg][Pb][16 B] | X [half][nkg][Px][16 B]
@@ -574,6 +581,7 @@ struct WgradFinalizeAll {
     } L[kTrainMaxLayers];
 };
 __global__ void __launch_bounds__(256) wgrad_finalize_kernel(const WgradFinalizeAll f) {
+    pdl_entry();
     const auto& L = f.L[blockIdx.y];
     const long long total = static_cast<long long>(L.cout) * L.cin * 9;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -613,6 +621,7 @@ __device__ __forceinline__ void pack_store_bf16(uint8_t* out, float v, int co, i
     *reinterpret_cast<__nv_bfloat16*>(out + base + cout_tile * 16 + off) = l;
 }
 __global__ void __launch_bounds__(256) pack_train_weights_kernel(const PackTrainAll f) {
+    pdl_entry();
     const auto& L = f.L[blockIdx.y];
     const long long total = static_cast<long long>(L.cout) * L.cin * 9;
     for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
@@ -629,6 +638,7 @@ __global__ void __launch_bounds__(256) pack_train_weights_kernel(const PackTrain
 // ---- Adam(amsgrad) with the step count and learning rate in device memory (CUDA-graph friendly) ----------------------
 // state[0] = step (as float, incremented here), state[1] = lr; hyper[0..1] receive step_size and 1/sqrt(bc2)
 __global__ void adam_prepare_kernel(float* __restrict__ state, float beta1, float beta2, float* __restrict__ hyper) {
+    pdl_entry();
     const double step = static_cast<double>(state[0]) + 1.0;
     state[0] = static_cast<float>(step);
     const double bc1 = 1.0 - pow(static_cast<double>(beta1), step);
@@ -641,6 +651,7 @@ __global__ void __launch_bounds__(256) adam_amsgrad_dev_kernel(float* __restrict
                                                                float* __restrict__ vmax, long long n,
                                                                const float* __restrict__ hyper, float beta1, float beta2,
                                                                float eps, float weight_decay, float grad_scale) {
+    pdl_entry();
     const float step_size = hyper[0], inv_bc2_sqrt = hyper[1];
     for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<long long>(gridDim.x) * blockDim.x) {

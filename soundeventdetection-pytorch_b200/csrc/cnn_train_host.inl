@@ -276,7 +276,7 @@ int sedb_cnn_train_forward(sedb_cnn_t* m, float* const* t, int n_tensors, const 
             max_total = std::max(max_total, static_cast<long long>(L.cout) * L.cin * L.ntaps);
         }
         dim3 pgrid(static_cast<unsigned>(std::min<long long>((max_total + 255) / 256, 148)), nl);
-        sedb::pack_train_weights_kernel<<<pgrid, 256, 0, st>>>(pk);
+        CUDA_TRY(launch_pdl(sedb::pack_train_weights_kernel, dim3(pgrid), dim3(256), 0, st, pk));
         g_launches.fetch_add(1);
     }
     CUDA_TRY(cudaGetLastError());
@@ -294,11 +294,11 @@ int sedb_cnn_train_forward(sedb_cnn_t* m, float* const* t, int n_tensors, const 
             if (!px4 && blocks > 148LL * 16) blocks = 148LL * 16;
             const size_t smem = static_cast<size_t>(tl.cout) * 11 * sizeof(float);
             if (px4)
-                sedb::conv_in2d_px4_kernel<1><<<static_cast<int>(blocks), 256, smem, st>>>(
-                    x_dev, q[0], nullptr, nullptr, ws + tl.Z.offset, n_img, tl.H, tl.W, tl.cout, tl.Z.S);
+                CUDA_TRY(launch_pdl(sedb::conv_in2d_px4_kernel<1>, dim3(static_cast<int>(blocks)), dim3(256), smem, st, 
+                    x_dev, q[0], nullptr, nullptr, ws + tl.Z.offset, n_img, tl.H, tl.W, tl.cout, tl.Z.S));
             else
-                sedb::conv_in2d_kernel<1><<<static_cast<int>(blocks), 256, smem, st>>>(
-                    x_dev, q[0], nullptr, nullptr, ws + tl.Z.offset, n_img, tl.H, tl.W, tl.cout, tl.Z.S);
+                CUDA_TRY(launch_pdl(sedb::conv_in2d_kernel<1>, dim3(static_cast<int>(blocks)), dim3(256), smem, st, 
+                    x_dev, q[0], nullptr, nullptr, ws + tl.Z.offset, n_img, tl.H, tl.W, tl.cout, tl.Z.S));
             g_launches.fetch_add(1);
         } else {
             if (int rc = launch_umma_layer<1>(m->ctx, m->train->wpack_fwd[l - 1], 1, 0, nullptr, nullptr, tl.fwd,
@@ -308,12 +308,12 @@ int sedb_cnn_train_forward(sedb_cnn_t* m, float* const* t, int n_tensors, const 
         }
         const long long px = static_cast<long long>(n_img) * tl.H * tl.W;
         dim3 sgrid(ew_blocks(px, 64), tl.cout / 8);
-        sedb::bn_stats_kernel<<<sgrid, 256, 0, st>>>(reinterpret_cast<const float*>(ws + tl.Z.offset), n_img, tl.cout, tl.H,
-                                                    tl.W, tl.Z.S, stats + tl.sums_off);
+        CUDA_TRY(launch_pdl(sedb::bn_stats_kernel, dim3(sgrid), dim3(256), 0, st, reinterpret_cast<const float*>(ws + tl.Z.offset), n_img, tl.cout, tl.H,
+                                                    tl.W, tl.Z.S, stats + tl.sums_off));
         const long long units = static_cast<long long>(n_img) * tl.A.H * tl.A.W * (tl.cout / 8);
-        sedb::bn_apply_kernel<<<ew_blocks(units), 256, 2 * tl.cout * sizeof(float), st>>>(
+        CUDA_TRY(launch_pdl(sedb::bn_apply_kernel, dim3(ew_blocks(units)), dim3(256), 2 * tl.cout * sizeof(float), st, 
             reinterpret_cast<const float*>(ws + tl.Z.offset), stats + tl.sums_off, gamma, beta, rmean, rvar, momentum, n_img,
-            tl.cout, tl.H, tl.W, tl.Z.S, tl.pool, tl.A.S, ws + tl.A.offset);
+            tl.cout, tl.H, tl.W, tl.Z.S, tl.pool, tl.A.S, ws + tl.A.offset));
         g_launches.fetch_add(2);
         CUDA_TRY(cudaGetLastError());
     }
@@ -321,9 +321,9 @@ int sedb_cnn_train_forward(sedb_cnn_t* m, float* const* t, int n_tensors, const 
         const TrainLayer& tl = plan.L[nl];
         const long long warps = static_cast<long long>(n_img) * plan.Hf;
         const int blocks = static_cast<int>((warps * 32 + 255) / 256);
-        sedb::head2d_kernel<1><<<blocks, 256, 0, st>>>(ws + tl.A.offset, t[10 * m->n_blocks], t[10 * m->n_blocks + 1],
+        CUDA_TRY(launch_pdl(sedb::head2d_kernel<1>, dim3(blocks), dim3(256), 0, st, ws + tl.A.offset, t[10 * m->n_blocks], t[10 * m->n_blocks + 1],
                                                       logits_dev, nullptr, n_img, tl.cout, plan.Hf, plan.Wf, tl.A.S,
-                                                      m->classes, m->ratio);
+                                                      m->classes, m->ratio));
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
     }
@@ -365,9 +365,9 @@ int sedb_cnn_train_backward(sedb_cnn_t* m, float* const* t, int n_tensors, const
         const TrainLayer& tl = plan.L[nl];
         const long long warps = static_cast<long long>(n_img) * plan.Hf;
         const int blocks = static_cast<int>((warps * 32 + 255) / 256);
-        sedb::head2d_bwd_kernel<<<blocks, 256, 0, st>>>(ws + tl.A.offset, t[10 * nb], dlogits_dev, d_fc_w, d_fc_b, G, n_img,
+        CUDA_TRY(launch_pdl(sedb::head2d_bwd_kernel, dim3(blocks), dim3(256), 0, st, ws + tl.A.offset, t[10 * nb], dlogits_dev, d_fc_w, d_fc_b, G, n_img,
                                                        tl.cout, plan.Hf, plan.Wf, tl.A.S, final_plane_S(0, plan.Hf, plan.Wf),
-                                                       m->classes, m->ratio);
+                                                       m->classes, m->ratio));
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
     }
@@ -383,21 +383,21 @@ int sedb_cnn_train_backward(sedb_cnn_t* m, float* const* t, int n_tensors, const
         const int S_g = final_plane_S(0, tl.A.H, tl.A.W);
         const long long px = static_cast<long long>(n_img) * tl.H * tl.W;
         dim3 rgrid(ew_blocks(px, 64), tl.cout / 8);
-        sedb::bn_bwd_reduce_kernel<<<rgrid, 256, 0, st>>>(Z, G, stats + tl.sums_off, gamma, beta, n_img, tl.cout, tl.H, tl.W,
-                                                         tl.Z.S, tl.pool, S_g, stats + tl.sums_off + 2 * tl.cout);
+        CUDA_TRY(launch_pdl(sedb::bn_bwd_reduce_kernel, dim3(rgrid), dim3(256), 0, st, Z, G, stats + tl.sums_off, gamma, beta, n_img, tl.cout, tl.H, tl.W,
+                                                         tl.Z.S, tl.pool, S_g, stats + tl.sums_off + 2 * tl.cout));
         dim3 agrid(ew_blocks(px, 128), tl.cout / 8);
         if (l == 0) {
-            sedb::bn_bwd_apply_kernel<1><<<agrid, 256, 0, st>>>(Z, G, stats + tl.sums_off, stats + tl.sums_off + 2 * tl.cout,
+            CUDA_TRY(launch_pdl(sedb::bn_bwd_apply_kernel<1>, dim3(agrid), dim3(256), 0, st, Z, G, stats + tl.sums_off, stats + tl.sums_off + 2 * tl.cout,
                                                                gamma, beta, n_img, tl.cout, tl.H, tl.W, tl.Z.S, tl.pool, S_g,
-                                                               0, nullptr, d_gamma, d_beta, x_dev, d_w);
+                                                               0, nullptr, d_gamma, d_beta, x_dev, d_w));
             g_launches.fetch_add(2);
             CUDA_TRY(cudaGetLastError());
             break;
         }
         if (l > sedb::kTrainMaxLayers) return fail("too many conv layers for the training step");
-        sedb::bn_bwd_apply_kernel<0><<<agrid, 256, 0, st>>>(Z, G, stats + tl.sums_off, stats + tl.sums_off + 2 * tl.cout, gamma,
+        CUDA_TRY(launch_pdl(sedb::bn_bwd_apply_kernel<0>, dim3(agrid), dim3(256), 0, st, Z, G, stats + tl.sums_off, stats + tl.sums_off + 2 * tl.cout, gamma,
                                                            beta, n_img, tl.cout, tl.H, tl.W, tl.Z.S, tl.pool, S_g, tl.dZ.S,
-                                                           ws + tl.dZ.offset, d_gamma, d_beta, nullptr, nullptr);
+                                                           ws + tl.dZ.offset, d_gamma, d_beta, nullptr, nullptr));
         g_launches.fetch_add(2);
         // weight gradient
         sedb::WgradParams wp = tl.wg;
@@ -407,7 +407,7 @@ int sedb_cnn_train_backward(sedb_cnn_t* m, float* const* t, int n_tensors, const
         wp.S_dz = tl.dZ.S;
         wp.S_x = plan.L[l - 1].A.S;
         dim3 wgrid(wp.n_pc, 3, tl.wg_tiles);
-        sedb::wgrad_umma_kernel<<<wgrid, sedb::kWgThreads, tl.wg_smem, st>>>(wp);
+        CUDA_TRY(launch_pdl(sedb::wgrad_umma_kernel, dim3(wgrid), dim3(sedb::kWgThreads), tl.wg_smem, st, wp));
         fin.L[l - 1].part = wp.part;
         fin.L[l - 1].d_w = d_w;
         fin.L[l - 1].n_pc = wp.n_pc;
@@ -425,7 +425,7 @@ int sedb_cnn_train_backward(sedb_cnn_t* m, float* const* t, int n_tensors, const
         long long max_total = 0;
         for (int i = 0; i < nl; ++i) max_total = std::max(max_total, static_cast<long long>(fin.L[i].cout) * fin.L[i].cin * 9);
         dim3 fgrid(static_cast<unsigned>(std::min<long long>((max_total + 255) / 256, 148)), nl);
-        sedb::wgrad_finalize_kernel<<<fgrid, 256, 0, st>>>(fin);
+        CUDA_TRY(launch_pdl(sedb::wgrad_finalize_kernel, dim3(fgrid), dim3(256), 0, st, fin));
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
     }
@@ -436,9 +436,9 @@ int sedb_bce_with_logits(const float* logits_dev, const float* target_dev, long 
                          int K, float pos_weight, float grad_scale, float* loss_dev, float* dlogits_dev, void* stream) {
     if (!logits_dev || !target_dev || (!loss_dev && !dlogits_dev)) return fail("sedb_bce_with_logits: null argument");
     if (B < 1 || F_out < 1 || F_tgt < 1 || K < 1 || B * F_out * K > (1LL << 30)) return fail("sedb_bce_with_logits: bad shape");
-    sedb::bce_logits_kernel<<<1, 1024, 0, static_cast<cudaStream_t>(stream)>>>(
+    CUDA_TRY(launch_pdl(sedb::bce_logits_kernel, dim3(1), dim3(1024), 0, static_cast<cudaStream_t>(stream), 
         logits_dev, target_dev, static_cast<int>(B), static_cast<int>(F_out), static_cast<int>(F_tgt), K, pos_weight,
-        grad_scale, loss_dev, dlogits_dev);
+        grad_scale, loss_dev, dlogits_dev));
     g_launches.fetch_add(1);
     CUDA_TRY(cudaGetLastError());
     return 0;
@@ -451,15 +451,15 @@ int sedb_adam_amsgrad_step_dev(float* param_dev, const float* grad_dev, float* e
     if (!param_dev || !grad_dev || !exp_avg_dev || !exp_avg_sq_dev || !max_exp_avg_sq_dev || !state_dev || !hyper_dev)
         return fail("null buffer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    sedb::adam_prepare_kernel<<<1, 1, 0, st>>>(state_dev, beta1, beta2, hyper_dev);
+    CUDA_TRY(launch_pdl(sedb::adam_prepare_kernel, dim3(1), dim3(1), 0, st, state_dev, beta1, beta2, hyper_dev));
     g_launches.fetch_add(1);
     if (n > 0) {
         long long blocks = (n + 255) / 256;
         if (blocks > 148 * 8) blocks = 148 * 8;
-        sedb::adam_amsgrad_dev_kernel<<<static_cast<int>(blocks), 256, 0, st>>>(param_dev, grad_dev, exp_avg_dev,
+        CUDA_TRY(launch_pdl(sedb::adam_amsgrad_dev_kernel, dim3(static_cast<int>(blocks)), dim3(256), 0, st, param_dev, grad_dev, exp_avg_dev,
                                                                                exp_avg_sq_dev, max_exp_avg_sq_dev, n,
                                                                                hyper_dev, beta1, beta2, eps, weight_decay,
-                                                                               grad_scale);
+                                                                               grad_scale));
         g_launches.fetch_add(1);
     }
     CUDA_TRY(cudaGetLastError());

@@ -131,6 +131,16 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
     }
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// First statement of a kernel that is launched with cudaLaunchAttributeProgrammaticStreamSerialization (launch_pdl in
+// cnn_host.inl): lets the NEXT kernel of the stream be placed as this grid's CTAs retire, then waits until the PREVIOUS
+// grid has completed and its memory operations are visible.  Both are no-ops for an ordinary launch.  Every thread of a
+// kernel launched that way must pass through the wait before it touches global memory.
+__device__ __forceinline__ void pdl_entry() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // ------------------------------------------------------------------ proxy fences
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() {
