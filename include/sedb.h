@@ -71,7 +71,11 @@ int sedb_mel_filterbank(float* out_host);
  * within 1e-2 dB of the reference; a bin further down is reported no lower than the reference minus 1e-2 dB and at most at
  * the DFT's own noise floor (about 100 dB below the frame's loudest bin).  Real recordings stay inside the window (16-bit
  * PCM quantisation noise under a full-scale tone sits 110-125 dB down: measured error there ~0.1 dB, see
- * tests/test_gpu_logmel.py::test_dynamic_range_contract_*). */
+ * tests/test_gpu_logmel.py::test_dynamic_range_contract_*).
+ * Reproducibility.  A frame's result is a function of the frame's samples alone: bit-identical whichever batch the clip
+ * arrives in, wherever it sits in it and however its buffer is aligned (the block scale is the exponent bucket of the
+ * frame's abs-max; the kernel usually knows it from the half the frame shares with the previous one and repeats the first
+ * DFT stage of the few frames where the other half is louder by a scale step). */
 int sedb_logmel_f32(sedb_ctx_t* ctx, const float* wave_dev, long long n_clips, long long n_samples,
                     long long wave_stride, const float* norm_dev, float* out_dev, void* stream);
 
