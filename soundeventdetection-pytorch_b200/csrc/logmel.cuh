@@ -51,6 +51,9 @@
 #ifndef SEDB_ROW128_FOLD
 #define SEDB_ROW128_FOLD 1
 #endif
+#ifndef SEDB_ROW128_EARLY
+#define SEDB_ROW128_EARLY 0
+#endif
 #ifndef SEDB_KAHEAD
 #define SEDB_KAHEAD 2
 #endif
@@ -991,6 +994,53 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 v_s[tid] = acc;                                       // Y[n2,128] (scaled)
             }
 #endif
+            // row k1 = 128: X[128 + 256 k2] = sum_n2 Y[n2,128] exp(-2 pi i n2 (2 k2+1)/256), k2 in [0,64); returns |X|^2
+            float2* spec_row = nullptr;
+            if (MODE == 1) spec_row = prm.spec + (static_cast<long long>(clip) * prm.n_frames + t) * kBins;
+            auto row128 = [&]() -> float {
+                float p128;
+
+                const int k2 = tid >> 3;
+                const int part = tid & 7;
+                float ar = 0.f, ai = 0.f;
+                const int mm = 2 * k2 + 1;
+#if SEDB_ROW128_FOLD
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int n2 = part + 8 * i;                      // interleaved: table reads spread over banks
+                    const float2 w = cs_s[(n2 * mm) & 255];
+                    ar = fmaf(v_s[n2], w.x, ar);
+                    ai = fmaf(v_s[64 + n2], w.y, ai);
+                }
+                if (part == 0) ai += (k2 & 1) ? red_s[28] : -red_s[28];   // - i Y[64] sin(pi (2 k2 + 1) / 2)
+#else
+#pragma unroll 8
+                for (int i = 0; i < 16; ++i) {
+                    const int n2 = part + 8 * i;                      // interleaved: table reads spread over banks
+                    const float2 w = cs_s[(n2 * mm) & 255];
+                    const float v = v_s[n2];
+                    ar = fmaf(v, w.x, ar);
+                    ai = fmaf(v, w.y, ai);
+                }
+#endif
+#pragma unroll
+                for (int o = 1; o < 8; o <<= 1) {
+                    ar += __shfl_xor_sync(0xffffffffu, ar, o);
+                    ai += __shfl_xor_sync(0xffffffffu, ai, o);
+                }
+                p128 = ar * ar + ai * ai;
+                if (MODE == 1 && part == 0) spec_row[128 + 256 * k2] = make_float2(ar * inv_scale, ai * inv_scale);
+                return p128;
+            };
+#if SEDB_ROW128_EARLY
+            // in the stage-1 MMA drain (the workers would only wait there); the result is parked in alt_s -- free once the
+            // sums above are through -- by the thread that stores it into the spectrum later
+            worker_sync();                                            // v_s (written by warps 0-2) visible, alt_s read
+            {
+                const float p128e = row128();
+                if (MODE == 0 && (tid & 7) == 0) alt_s[tid >> 3] = p128e;
+            }
+#endif
             mbar_wait(d1_full, attempt & 1);
             ++attempt;
             tc_fence_after();
@@ -1059,44 +1109,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                 if (lane == 0) mbar_arrive(&full2[c]);
             }
             SEDB_PROF(3);   // twiddle / radix-2 / split
-            // row k1 = 128 while the stage-2 MMAs drain: X[128 + 256 k2] = sum_n2 Y[n2,128] exp(-2 pi i n2 (2 k2+1)/256),
-            // k2 in [0,64).  The power goes to the spectrum after d2_full (it aliases the operand ring until then).
-            float2* spec_row = nullptr;
-            if (MODE == 1) spec_row = prm.spec + (static_cast<long long>(clip) * prm.n_frames + t) * kBins;
-            worker_sync();                                            // v_s (written by warps 0-3) visible
-            float p128 = 0.f;
-            {
-                const int k2 = tid >> 3;
-                const int part = tid & 7;
-                float ar = 0.f, ai = 0.f;
-                const int mm = 2 * k2 + 1;
-#if SEDB_ROW128_FOLD
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int n2 = part + 8 * i;                      // interleaved: table reads spread over banks
-                    const float2 w = cs_s[(n2 * mm) & 255];
-                    ar = fmaf(v_s[n2], w.x, ar);
-                    ai = fmaf(v_s[64 + n2], w.y, ai);
-                }
-                if (part == 0) ai += (k2 & 1) ? red_s[28] : -red_s[28];   // - i Y[64] sin(pi (2 k2 + 1) / 2)
-#else
-#pragma unroll 8
-                for (int i = 0; i < 16; ++i) {
-                    const int n2 = part + 8 * i;                      // interleaved: table reads spread over banks
-                    const float2 w = cs_s[(n2 * mm) & 255];
-                    const float v = v_s[n2];
-                    ar = fmaf(v, w.x, ar);
-                    ai = fmaf(v, w.y, ai);
-                }
+#if !SEDB_ROW128_EARLY
+            // (in the stage-2 MMA drain; the power goes to the spectrum after d2_full: it aliases the operand ring until then)
+            worker_sync();                                            // v_s (written by warps 0-2) visible
+            const float p128 = row128();
 #endif
-#pragma unroll
-                for (int o = 1; o < 8; o <<= 1) {
-                    ar += __shfl_xor_sync(0xffffffffu, ar, o);
-                    ai += __shfl_xor_sync(0xffffffffu, ai, o);
-                }
-                p128 = ar * ar + ai * ai;
-                if (MODE == 1 && part == 0) spec_row[128 + 256 * k2] = make_float2(ar * inv_scale, ai * inv_scale);
-            }
             SEDB_PROF(6);   // row 128
             // ---------------------------------------------------------------- power spectrum / complex output
             mbar_wait(d2_full, it & 1);
@@ -1155,7 +1172,11 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                     }
                 }
             }
+#if SEDB_ROW128_EARLY
+            if (MODE == 0 && (tid & 7) == 0) p_s[128 + 256 * (tid >> 3)] = alt_s[tid >> 3];
+#else
             if (MODE == 0 && (tid & 7) == 0) p_s[128 + 256 * (tid >> 3)] = p128;
+#endif
             SEDB_PROF(5);   // power spectrum
             tc_fence_before();
             if (MODE == 0) {

@@ -1,4 +1,3 @@
-timeout 1500 python -m pytest tests -q -m gpu -x 2>&1 | tail -4
-timeout 900 python bench.py --no-cpu-baseline > gpurun_out/bench_r2f.json 2> gpurun_out/bench_r2f.err; python -c "
-import json; d=json.load(open('gpurun_out/bench_r2f.json')); print(d['value'], d['ms_per_step'], d['config']['stage_ms'], d['config4']['ms_per_step'], d['config4']['split_ms_eager'], d['config3']['ms_per_step'], d['config5']['frames_128']['ms_per_step'])"
-tail -3 gpurun_out/bench_r2f.err
+for v in 0 1 0 1; do SEDB_LIB_PATH=$PWD/tests/dev/lib_e$v.so timeout 300 python tests/dev/lm_time.py 256 2>&1 | tail -1; sleep 2; done
+SEDB_LIB_PATH=$PWD/tests/dev/lib_e1.so timeout 900 python -m pytest tests/test_gpu_logmel.py tests/test_gpu_pcm16.py -x -q -m gpu 2>&1 | tail -3
+SEDB_LIB_PATH=$PWD/tests/dev/lib_e1.so timeout 300 python tests/dev/phase_prof.py 256 2>/dev/null | head -13
