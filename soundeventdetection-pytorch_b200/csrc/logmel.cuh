@@ -54,6 +54,9 @@
 #ifndef SEDB_ROW128_EARLY
 #define SEDB_ROW128_EARLY 0
 #endif
+#ifndef SEDB_MMA_UNROLL
+#define SEDB_MMA_UNROLL 1
+#endif
 #ifndef SEDB_KAHEAD
 #define SEDB_KAHEAD 2
 #endif
@@ -515,11 +518,19 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
         for (int it = 0; it < n_iter; ++it) {
             // ---------------- stage 1: 8 K-chunks of 16 folded rows (m); repeated when the workers reject the attempt
             for (;;) {
-#pragma unroll 1
+                constexpr int kMmaUnroll = SEDB_MMA_UNROLL;          // 8: slot, parity and descriptors are immediates
+#pragma unroll kMmaUnroll
                 for (int c = 0; c < 8; ++c) {
                     const int s = c & (kNumSlots - 1);
                     const int u = c / kNumSlots;
+#ifdef SEDB_PROF_MMA
+                    long long tm0 = clock64();
+#endif
                     mbar_wait(&full1[s], u & 1);
+#ifdef SEDB_PROF_MMA
+                    long long tm1 = clock64();
+                    if (prm.prof != nullptr && lane == 0) atomicAdd(prm.prof + (c == 7 ? 13 : 12), static_cast<unsigned long long>(tm1 - tm0));
+#endif
 #if SEDB_CONSUMER_FENCE
                     if (!SEDB_TAIL_FENCE || c < 7) fence_proxy_async_smem();
 #endif
@@ -537,6 +548,9 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                         if (c == 7) umma_commit(d1_full);
                     }
                     __syncwarp();
+#ifdef SEDB_PROF_MMA
+                    if (prm.prof != nullptr && lane == 0) atomicAdd(prm.prof + 14, static_cast<unsigned long long>(clock64() - tm1));
+#endif
                 }
 #if SEDB_SPLIT_FP16
                 mbar_wait(dec, attempt & 1);
@@ -547,7 +561,8 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
 #endif
             }
             // ---------------- stage 2: 4 K-chunks of 16 columns (n), even and odd outputs; A operand from TMEM
-#pragma unroll 1
+            constexpr int kMmaUnroll2 = SEDB_MMA_UNROLL >= 4 ? 4 : 1;
+#pragma unroll kMmaUnroll2
             for (int j = 0; j < 4; ++j) {
                 mbar_wait(&full2[j], it & 1);
                 tc_fence_after();

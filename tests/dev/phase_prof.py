@@ -18,7 +18,7 @@ e0.record(); P.waveform_to_log_mel(w); e1.record(); torch.cuda.synchronize()
 out = np.zeros(128, dtype=np.uint64)
 lib.sedb_debug_phase_profile(0, ctypes.c_void_p(out.ctypes.data))
 frames = B * 182
-names = ["load+scale", "fold/split", "wait S1", "twiddle/radix2", "wait S2", "power", "row128", "final sync", "sync->mel", "mel partials", "sync", "finalize", "fold: data wait", "fold: slot wait", "fold: store+fence+arrive"]
+names = ["load+scale", "fold/split", "wait S1", "twiddle/radix2", "wait S2", "power", "row128", "final sync", "sync->mel", "mel partials", "sync", "finalize", "aux 12", "aux 13", "aux 14"]
 tot = out[:12].sum()
 print(f"B={B} {e0.elapsed_time(e1):.3f} ms; cycles/frame total {tot/frames:.0f}")
 for n, v in zip(names, out[:15]): print(f"  {n:16s} {v/frames:8.0f} cyc/frame  {100*v/tot:5.1f}%")
