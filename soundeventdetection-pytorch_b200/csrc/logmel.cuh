@@ -398,12 +398,17 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
     }
     for (int i = tid; i < kMelTabEntries; i += kThreads) mel_tab_s[i] = prm.mel_tab[i];
     for (int i = tid; i < 4 * kMel; i += kThreads) coef_s[i] = prm.mel_w[i];
-    if (prm.norm != nullptr)
-        for (int i = tid; i < 2 * kMel; i += kThreads) norm_s[i] = prm.norm[i];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_ptr_s;
+    // Set-up done (tables above are the context's own constants).  Launched with programmatic stream serialization, the
+    // kernel may have been placed before its predecessor finished: wait for it before touching the caller's buffers.
+    pdl_entry();
+    if (prm.norm != nullptr) {
+        for (int i = tid; i < 2 * kMel; i += kThreads) norm_s[i] = prm.norm[i];
+        __syncthreads();
+    }
 
     // Frame schedule: CTA b owns the CONSECUTIVE frames [f0, f0 + n_iter) of the flattened (clip, frame) sequence.  Two
     // consecutive frames of a clip share half their samples (hop = window / 2), so the second read of a sample hits L2
@@ -791,9 +796,10 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                     }
                 } else {
 #pragma unroll 1
-                    for (int c = 0; c < 8; ++c) {
-                        mA = absmax4(mA, cvt(load_a_gen(c)));
-                        mB = absmax4(mB, cvt(load_b_gen(c)));
+                    for (int c = 0; c < 8; c += 2) {                         // two chunks of loads in flight
+                        const Raw a0 = load_a_gen(c), b0 = load_b_gen(c), a1 = load_a_gen(c + 1), b1 = load_b_gen(c + 1);
+                        mA = absmax4(absmax4(mA, cvt(a0)), cvt(a1));
+                        mB = absmax4(absmax4(mB, cvt(b0)), cvt(b1));
                     }
                 }
 #pragma unroll
@@ -933,10 +939,15 @@ __global__ void __launch_bounds__(kThreads, 1) logmel_fused_kernel(const LogmelP
                         }
                         fold_chunk(c, cvt(qa[c]), cvt(qb[c]));
                     }
-                } else {                                              // edge frames: a compact loop
+                } else {                                              // edge frames: a compact loop, one chunk requested ahead
+                    Raw na = load_a_gen(0), nb = load_b_gen(0);
 #pragma unroll 1
                     for (int c = 0; c < 8; ++c) {
-                        const Raw a = load_a_gen(c), b = load_b_gen(c);
+                        const Raw a = na, b = nb;
+                        if (c < 7) {
+                            na = load_a_gen(c + 1);
+                            nb = load_b_gen(c + 1);
+                        }
                         fold_chunk(c, cvt(a), cvt(b));
                     }
                 }

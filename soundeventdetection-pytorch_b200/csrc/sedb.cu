@@ -225,21 +225,24 @@ static int launch_logmel(sedb_ctx_t* c, int mode, const void* wave, long long n_
     p.prof = g_prof;
     const long long total = n_clips * p.n_frames;
     const int grid = static_cast<int>(total < c->num_sms ? total : c->num_sms);
+    const dim3 g(static_cast<unsigned>(grid)), b(sedb::kThreads);
+    cudaError_t le = cudaSuccess;
     if (mode == 0 && in_fmt == 0)
-        sedb::logmel_fused_kernel<0, 0><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
+        le = launch_pdl(sedb::logmel_fused_kernel<0, 0>, g, b, sedb::kSmemBytes, st, p);
     else if (mode == 0 && n_channels == 1)
-        sedb::logmel_fused_kernel<0, 1><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
+        le = launch_pdl(sedb::logmel_fused_kernel<0, 1>, g, b, sedb::kSmemBytes, st, p);
     else if (mode == 0 && n_channels == 2)
-        sedb::logmel_fused_kernel<0, 2><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
+        le = launch_pdl(sedb::logmel_fused_kernel<0, 2>, g, b, sedb::kSmemBytes, st, p);
     else if (mode == 0 && n_channels == 4)
-        sedb::logmel_fused_kernel<0, 4><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
+        le = launch_pdl(sedb::logmel_fused_kernel<0, 4>, g, b, sedb::kSmemBytes, st, p);
     else if (mode == 0)
-        sedb::logmel_fused_kernel<0, sedb::kInPcmAny><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
+        le = launch_pdl(sedb::logmel_fused_kernel<0, sedb::kInPcmAny>, g, b, sedb::kSmemBytes, st, p);
     else if (in_fmt == 0)
-        sedb::logmel_fused_kernel<1, 0><<<grid, sedb::kThreads, sedb::kSmemBytes, st>>>(p);
+        le = launch_pdl(sedb::logmel_fused_kernel<1, 0>, g, b, sedb::kSmemBytes, st, p);
     else
         return fail("the complex STFT output takes float32 input");
     g_launches.fetch_add(1);
+    CUDA_TRY(le);
     CUDA_TRY(cudaGetLastError());
     return 0;
 }
