@@ -1,6 +1,10 @@
 // Host side of the Cnn_AvgPooling training step (included by sedb.cu after cnn_host.inl): per-shape plan, buffers,
 // launches of cnn_train.cuh.  Reference: train.py:96-103, models/spectogram_models.py:153-160,185-202.
 
+#ifndef SEDB_WGRAD_SIDE_STREAM
+#define SEDB_WGRAD_SIDE_STREAM 1
+#endif
+
 namespace {
 
 struct TrainLayer {               // conv layer l = 0 .. nl (0 = block0.conv1 on CUDA cores)
@@ -67,12 +71,22 @@ struct sedb_cnn_train {
     std::map<std::pair<long long, long long>, TrainPlan> plans;
     std::vector<uint8_t*> wpack_fwd, wpack_dgrad;     // per umma layer: bf16 hi|lo packs (forward / data-gradient convolution)
     ZeroedSet zeroed;
+    // The weight-gradient GEMM of a layer only needs dZ_l and A_{l-1}; nothing downstream of it but the final reduction
+    // reads its output.  It runs on a stream of its own, forked off the caller's stream once dZ_l is written and joined
+    // before wgrad_finalize, so the (latency-bound) weight gradients overlap the data-gradient / BatchNorm chain.  The
+    // fork / join is by events, which a stream capture (the trainer's CUDA graph) turns into graph edges.
+    cudaStream_t s_wgrad = nullptr;
+    std::vector<cudaEvent_t> ev_fork;                  // one per umma layer
+    cudaEvent_t ev_join = nullptr;
 };
 
 static void sedb_cnn_train_free(sedb_cnn* m) {
     if (!m || !m->train) return;
     for (auto p : m->train->wpack_fwd) cudaFree(p);
     for (auto p : m->train->wpack_dgrad) cudaFree(p);
+    for (auto e : m->train->ev_fork) cudaEventDestroy(e);
+    if (m->train->ev_join) cudaEventDestroy(m->train->ev_join);
+    if (m->train->s_wgrad) cudaStreamDestroy(m->train->s_wgrad);
     delete m->train;
     m->train = nullptr;
 }
@@ -94,6 +108,13 @@ static int cnn_train_state(sedb_cnn* m) {
         t->wpack_dgrad.push_back(b);
     }
     CUDA_TRY(cudaFuncSetAttribute(sedb::wgrad_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    CUDA_TRY(cudaStreamCreateWithFlags(&t->s_wgrad, cudaStreamNonBlocking));
+    for (size_t i = 0; i < m->layers.size(); ++i) {
+        cudaEvent_t e = nullptr;
+        CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        t->ev_fork.push_back(e);
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
     return 0;
 }
 
@@ -257,6 +278,7 @@ int sedb_cnn_train_forward(sedb_cnn_t* m, float* const* t, int n_tensors, const 
     const int nl = static_cast<int>(m->layers.size());
     // bf16 hi|lo packs of the current weights: forward convolution and its data-gradient transpose (one launch)
     if (nl > sedb::kTrainMaxLayers) return fail("too many conv layers for the training step");
+    bool pack_forked = false;
     {
         sedb::PackTrainAll pk;
         pk.n = nl;
@@ -276,11 +298,21 @@ int sedb_cnn_train_forward(sedb_cnn_t* m, float* const* t, int n_tensors, const 
             max_total = std::max(max_total, static_cast<long long>(L.cout) * L.cin * L.ntaps);
         }
         dim3 pgrid(static_cast<unsigned>(std::min<long long>((max_total + 255) / 256, 148)), nl);
-        CUDA_TRY(launch_pdl(sedb::pack_train_weights_kernel, dim3(pgrid), dim3(256), 0, st, pk));
+        if (SEDB_WGRAD_SIDE_STREAM) {
+            // the packs are first needed by layer 1: they are written on the side stream while layer 0 runs
+            CUDA_TRY(cudaEventRecord(m->train->ev_fork[0], st));
+            CUDA_TRY(cudaStreamWaitEvent(m->train->s_wgrad, m->train->ev_fork[0], 0));
+            sedb::pack_train_weights_kernel<<<pgrid, 256, 0, m->train->s_wgrad>>>(pk);
+            CUDA_TRY(cudaEventRecord(m->train->ev_join, m->train->s_wgrad));
+            pack_forked = true;
+        } else {
+            CUDA_TRY(launch_pdl(sedb::pack_train_weights_kernel, dim3(pgrid), dim3(256), 0, st, pk));
+        }
         g_launches.fetch_add(1);
     }
     CUDA_TRY(cudaGetLastError());
     for (int l = 0; l <= nl; ++l) {
+        if (l == 1 && pack_forked) CUDA_TRY(cudaStreamWaitEvent(st, m->train->ev_join, 0));
         const TrainLayer& tl = plan.L[l];
         float* const* q = t + 10 * tl.block;
         const float* gamma = q[2 + 4 * tl.which];
@@ -371,6 +403,7 @@ int sedb_cnn_train_backward(sedb_cnn_t* m, float* const* t, int n_tensors, const
         g_launches.fetch_add(1);
         CUDA_TRY(cudaGetLastError());
     }
+    bool forked = false;
     for (int l = nl; l >= 0; --l) {
         const TrainLayer& tl = plan.L[l];
         float* const* q = t + 10 * tl.block;
@@ -407,7 +440,14 @@ int sedb_cnn_train_backward(sedb_cnn_t* m, float* const* t, int n_tensors, const
         wp.S_dz = tl.dZ.S;
         wp.S_x = plan.L[l - 1].A.S;
         dim3 wgrid(wp.n_pc, 3, tl.wg_tiles);
-        CUDA_TRY(launch_pdl(sedb::wgrad_umma_kernel, dim3(wgrid), dim3(sedb::kWgThreads), tl.wg_smem, st, wp));
+        if (SEDB_WGRAD_SIDE_STREAM) {
+            CUDA_TRY(cudaEventRecord(m->train->ev_fork[l - 1], st));                 // dZ_l is complete on the caller's stream
+            CUDA_TRY(cudaStreamWaitEvent(m->train->s_wgrad, m->train->ev_fork[l - 1], 0));
+            sedb::wgrad_umma_kernel<<<wgrid, sedb::kWgThreads, tl.wg_smem, m->train->s_wgrad>>>(wp);
+            forked = true;
+        } else {
+            CUDA_TRY(launch_pdl(sedb::wgrad_umma_kernel, dim3(wgrid), dim3(sedb::kWgThreads), tl.wg_smem, st, wp));
+        }
         fin.L[l - 1].part = wp.part;
         fin.L[l - 1].d_w = d_w;
         fin.L[l - 1].n_pc = wp.n_pc;
@@ -420,6 +460,10 @@ int sedb_cnn_train_backward(sedb_cnn_t* m, float* const* t, int n_tensors, const
                                           ws + tl.dZ.offset, reinterpret_cast<uint8_t*>(G), n_img, tl.dZ.S,
                                           final_plane_S(0, tl.H, tl.W), st))
             return rc;
+    }
+    if (forked) {                                                    // join: the weight-gradient stream's partial sums
+        CUDA_TRY(cudaEventRecord(m->train->ev_join, m->train->s_wgrad));
+        CUDA_TRY(cudaStreamWaitEvent(st, m->train->ev_join, 0));
     }
     if (nl > 0) {                                                    // all weight gradients: partial sums -> gradient buffers
         long long max_total = 0;
