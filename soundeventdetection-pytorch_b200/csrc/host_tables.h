@@ -129,6 +129,37 @@ inline double bessel_i0(double x) {                  // power series; converges 
     }
     return sum;
 }
+// Compact form for the kernel: a phase's coefficients outside a window of `span` <= 2 width + 1 taps are the clamped
+// tails of the Kaiser window (|h| < 1e-21), so only [first[p], first[p] + span) of each phase is kept:
+// hc[k * ln + p] = h[(first[p] + k) * ln + p].
+inline void compact_resample_filters(const std::vector<float>& h, int ln, int taps, std::vector<float>& hc,
+                                     std::vector<int>& first, int& span) {
+    first.assign(ln, 0);
+    span = 1;
+    std::vector<int> last(ln, 0);
+    for (int p = 0; p < ln; ++p) {
+        int a = taps, b = -1;
+        for (int k = 0; k < taps; ++k)
+            if (std::fabs(h[static_cast<size_t>(k) * ln + p]) > 1e-12f) {
+                if (k < a) a = k;
+                b = k;
+            }
+        if (b < 0) a = b = 0;
+        first[p] = a;
+        last[p] = b;
+        if (b - a + 1 > span) span = b - a + 1;
+    }
+    if (4 * span > 3 * taps) {                      // nothing worth skipping (small Lo): keep every tap, no per-phase offsets
+        span = taps;
+        first.assign(ln, 0);
+    }
+    for (int p = 0; p < ln; ++p)
+        if (first[p] + span > taps) first[p] = taps - span;
+    hc.assign(static_cast<size_t>(span) * ln, 0.f);
+    for (int p = 0; p < ln; ++p)
+        for (int k = 0; k < span; ++k) hc[static_cast<size_t>(k) * ln + p] = h[static_cast<size_t>(first[p] + k) * ln + p];
+}
+
 inline std::vector<float> make_resample_filters(int lo, int ln, int& width, int& taps) {
     const double base = static_cast<double>(lo < ln ? lo : ln) * kResampleRolloff;
     width = static_cast<int>(std::ceil(kResampleZeros * static_cast<double>(lo) / base));

@@ -70,8 +70,8 @@ struct sedb_ctx {
     size_t d_probs_elems = 0;
     // polyphase filter tables of the sample-rate converter, one per reduced rate pair (built on first use)
     struct ResampleTable {
-        int lo = 0, ln = 0, width = 0, taps = 0;
-        float* h = nullptr;
+        int lo = 0, ln = 0, width = 0, taps = 0, span = 0;
+        float* h = nullptr;          // compact coefficients [span][ln], then first[ln] as int
     };
     std::vector<ResampleTable> resample_tables;
 };
@@ -304,7 +304,12 @@ int sedb_resample_f32(sedb_ctx_t* c, const float* in_dev, long long n_clips, lon
         sedb_ctx::ResampleTable t;
         t.lo = lo;
         t.ln = ln;
-        std::vector<float> h = sedb_host::make_resample_filters(lo, ln, t.width, t.taps);
+        std::vector<float> hfull = sedb_host::make_resample_filters(lo, ln, t.width, t.taps), h;
+        std::vector<int> first;
+        sedb_host::compact_resample_filters(hfull, ln, t.taps, h, first, t.span);
+        const size_t ncoef = h.size();
+        h.resize(ncoef + first.size());
+        std::memcpy(h.data() + ncoef, first.data(), first.size() * sizeof(int));
         CUDA_TRY(cudaMalloc(&t.h, h.size() * sizeof(float)));
         cudaError_t e = cudaMemcpy(t.h, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {
@@ -318,6 +323,8 @@ int sedb_resample_f32(sedb_ctx_t* c, const float* in_dev, long long n_clips, lon
     p.x = in_dev;
     p.y = out_dev;
     p.h = tab->h;
+    p.first = reinterpret_cast<const int*>(tab->h + static_cast<size_t>(tab->span) * ln);
+    p.span = tab->span;
     p.in_stride = in_stride;
     p.out_stride = out_stride;
     p.n_in = static_cast<int>(n_in);
