@@ -157,7 +157,11 @@ int sedb_cnn_forward(sedb_cnn_t* cnn, const float* x_dev, long long n_clips, lon
  * directly -- no load step; running_mean / running_var are written.
  * The workspace (sedb_cnn_train_workspace_bytes) carries the forward activations to the backward call: call backward
  * with the same workspace, shape and x_dev, before the next forward.  Same zero-padding contract as
- * sedb_cnn_forward (sedb_cnn_workspace_invalidate also forgets training workspaces). */
+ * sedb_cnn_forward (sedb_cnn_workspace_invalidate also forgets training workspaces).
+ * Streams.  Both calls are asynchronous on `stream`.  Internally the weight packing (forward) and the weight-gradient
+ * GEMMs (backward) run on a stream owned by the handle, forked from and joined back into `stream` with events before the
+ * call returns control of the results to `stream`; under stream capture the fork / join becomes graph edges.  One
+ * forward / backward pair per handle at a time. */
 size_t sedb_cnn_train_workspace_bytes(sedb_cnn_t* cnn, long long n_clips, long long T);
 int sedb_cnn_train_forward(sedb_cnn_t* cnn, float* const* tensors_dev, int n_tensors, const float* x_dev,
                            long long n_clips, long long T, float momentum, float* logits_dev, void* workspace_dev,
