@@ -19,6 +19,9 @@
 //   power, Hermitian bin map, mel filterbank in moment form (partial moments per <= 43-bin piece by the workers, the
 //   64 filters + 10 log10(max(1e-10, .)) + store by the two helper warps).
 // Warp roles: 16 workers (112 registers after setmaxnreg), MMA issuer, bulk-copy producer, 2 helpers (32 registers).
+// A CTA owns a run of CONSECUTIVE frames; the workers request a frame's samples two 16-row chunks ahead of the fold
+// (nothing of the frame is held in registers beyond that), and the fp16 block scale is taken from the half-frame shared
+// with the previous frame, checked once the other half has been seen, and the stage-1 attempt repeated if it was too large.
 // Input: fp32 mono (IN = 0) or interleaved 16-bit PCM with the channel mean fused into the loader (IN = 1, 2, 4, any).
 // GEMM operands are split x = hi + lo (two 16-bit floats) and multiplied as hi*hi + lo*hi + hi*lo with fp32
 // accumulation in TMEM: ~2^-17 relative with bf16 halves, ~2^-22 with fp16 halves (SEDB_SPLIT_FP16=1, which adds a
@@ -27,12 +30,19 @@
 #include "umma.cuh"
 #include <type_traits>
 
-// cp.async.bulk.prefetch.L2 of the next frame by the copy warp (0 disables it for A/B measurements: the frame-load
-// phase is 4.2 k cycles with it, 5.8 k without)
+// cp.async.bulk.prefetch.L2 of the next frame's new half by the copy warp (0 disables it for A/B measurements)
 #ifndef SEDB_L2_PREFETCH
 #define SEDB_L2_PREFETCH 1
 #endif
-// development switches of the worker loop (see the comments at their uses)
+// Development switches (defaults = the shipped configuration; measurements in profiles/r2_notes.md section 6):
+//   SEDB_CONSUMER_FENCE  fence.proxy.async by the MMA warp after its wait instead of by the 512 producers (which drains
+//                        their prefetched loads at every chunk)          SEDB_TAIL_FENCE  producer-side fence for the last chunk only
+//   SEDB_KAHEAD          chunks of loads in flight ahead of the fold      SEDB_HROW_PIPE   window row factors fetched a chunk ahead
+//   SEDB_TW_UNROLL       unroll of the twiddle loop (4 spills)            SEDB_MMA_UNROLL  unroll of the MMA warp's chunk loop
+//   SEDB_ROW128_FOLD     row-128 sums over folded inputs (64 terms)       SEDB_ROW128_EARLY  ... run in the stage-1 MMA drain
+//   SEDB_INCR_FRAME      incremental (clip, frame) instead of a 64-bit division per frame
+//   SEDB_RELAX_NS        nanosleep between the polls of the copy / helper warps
+//   -DSEDB_PROF_FOLD / -DSEDB_PROF_MMA / -DSEDB_DEBUG_SCALE  extra in-kernel counters and a per-frame printf
 #ifndef SEDB_CONSUMER_FENCE
 #define SEDB_CONSUMER_FENCE 1
 #endif
