@@ -160,6 +160,32 @@ inline void compact_resample_filters(const std::vector<float>& h, int ln, int ta
         for (int k = 0; k < span; ++k) hc[static_cast<size_t>(k) * ln + p] = h[static_cast<size_t>(first[p] + k) * ln + p];
 }
 
+// Tensor-core form (csrc/resample.cuh: resample_umma_kernel): per 16-tap K-step one block of [hi | lo] fp16 halves of
+// the filters scaled by 2^shift, each half npad x 16 in the canonical K-major no-swizzle operand layout
+// byte(n, k) = (n / 8) 128 + (k / 8) (npad / 8) 128 + (n % 8) 16 + (k % 8) 2  (rows n >= ln and taps >= `taps` are zero).
+inline std::vector<uint8_t> pack_resample_filters(const std::vector<float>& h, int ln, int taps, int shift, int& npad,
+                                                  int& nks) {
+    npad = (ln + 15) / 16 * 16;
+    nks = (taps + 15) / 16;
+    const size_t half = static_cast<size_t>(npad) * 32, chunk = 2 * half;
+    std::vector<uint8_t> out(chunk * nks, 0);
+    const float sc = std::ldexp(1.0f, shift);
+    for (int ks = 0; ks < nks; ++ks)
+        for (int n = 0; n < ln; ++n)
+            for (int k = 0; k < 16; ++k) {
+                const int tap = 16 * ks + k;
+                if (tap >= taps) continue;
+                const float v = h[static_cast<size_t>(tap) * ln + n] * sc;
+                const __half hi = __float2half_rn(v);
+                const __half lo = __float2half_rn(v - __half2float(hi));
+                const size_t off = static_cast<size_t>(n / 8) * 128 + static_cast<size_t>(k / 8) * (npad / 8) * 128 +
+                                   (n % 8) * 16 + (k % 8) * 2;
+                std::memcpy(&out[ks * chunk + off], &hi, 2);
+                std::memcpy(&out[ks * chunk + half + off], &lo, 2);
+            }
+    return out;
+}
+
 inline std::vector<float> make_resample_filters(int lo, int ln, int& width, int& taps) {
     const double base = static_cast<double>(lo < ln ? lo : ln) * kResampleRolloff;
     width = static_cast<int>(std::ceil(kResampleZeros * static_cast<double>(lo) / base));

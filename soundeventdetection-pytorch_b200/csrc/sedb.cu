@@ -72,6 +72,9 @@ struct sedb_ctx {
     struct ResampleTable {
         int lo = 0, ln = 0, width = 0, taps = 0, span = 0;
         float* h = nullptr;          // compact coefficients [span][ln], then first[ln] as int
+        uint8_t* hpack = nullptr;    // tensor-core form (pack_resample_filters); null when the rate pair does not qualify
+        int npad = 0, nks = 0;
+        size_t umma_smem = 0;
     };
     std::vector<ResampleTable> resample_tables;
 };
@@ -184,7 +187,10 @@ int sedb_destroy(sedb_ctx_t* c) {
     cudaFree(c->d_ws[0]);
     cudaFree(c->d_ws[1]);
     cudaFree(c->d_probs);
-    for (auto& t : c->resample_tables) cudaFree(t.h);
+    for (auto& t : c->resample_tables) {
+        cudaFree(t.h);
+        cudaFree(t.hpack);
+    }
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
     if (c->s_comp) cudaStreamDestroy(c->s_comp);
     delete c;
@@ -316,8 +322,56 @@ int sedb_resample_f32(sedb_ctx_t* c, const float* in_dev, long long n_clips, lon
             cudaFree(t.h);
             return fail("cudaMemcpy(resample filters): %s", cudaGetErrorString(e));
         }
+        // tensor-core path: N = phases <= 256, the tile's input span + rings must fit shared memory
+        {
+            int npad = 0, nks = 0;
+            std::vector<uint8_t> hp = sedb_host::pack_resample_filters(hfull, ln, t.taps, sedb::kRsFilterShift, npad, nks);
+            const size_t span_b = ((static_cast<size_t>(127) * lo + 16 * nks) * 4 + 127) / 128 * 128;
+            const size_t smem = span_b + static_cast<size_t>(sedb::kRsASlots) * 8192 + static_cast<size_t>(sedb::kRsBSlots) * npad * 64 + 256;
+            if (npad >= 64 && npad <= 256 && smem <= 220 * 1024) {       // (few phases: the CUDA-core FIR is faster)
+                e = cudaMalloc(&t.hpack, hp.size());
+                if (e == cudaSuccess) e = cudaMemcpy(t.hpack, hp.data(), hp.size(), cudaMemcpyHostToDevice);
+                if (e != cudaSuccess) {
+                    cudaFree(t.h);
+                    cudaFree(t.hpack);
+                    return fail("resample filters (tensor-core form): %s", cudaGetErrorString(e));
+                }
+                t.npad = npad;
+                t.nks = nks;
+                t.umma_smem = smem;
+            }
+        }
         c->resample_tables.push_back(t);
         tab = &c->resample_tables.back();
+    }
+    const long long n_blocks_all = (n_out + ln - 1) / ln;
+    static const bool force_fir = std::getenv("SEDB_RESAMPLE_FIR") != nullptr;
+    if (tab->hpack && !force_fir) {
+        sedb::ResampleUmmaParams q;
+        q.x = in_dev;
+        q.y = out_dev;
+        q.hpack = tab->hpack;
+        q.in_stride = in_stride;
+        q.out_stride = out_stride;
+        q.n_in = static_cast<int>(n_in);
+        q.n_out = static_cast<int>(n_out);
+        q.lo = lo;
+        q.ln = ln;
+        q.width = tab->width;
+        q.npad = tab->npad;
+        q.nks = tab->nks;
+        q.tiles_per_clip = static_cast<int>((n_blocks_all + 127) / 128);
+        const long long tiles = static_cast<long long>(q.tiles_per_clip) * n_clips;
+        if (tiles < (1LL << 31)) {
+            q.n_tiles = static_cast<int>(tiles);
+            CUDA_TRY(cudaFuncSetAttribute(sedb::resample_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          static_cast<int>(tab->umma_smem)));
+            const int grid = static_cast<int>(tiles < c->num_sms ? tiles : c->num_sms);
+            sedb::resample_umma_kernel<<<grid, sedb::kRsThreads, tab->umma_smem, st>>>(q);
+            g_launches.fetch_add(1);
+            CUDA_TRY(cudaGetLastError());
+            return 0;
+        }
     }
     sedb::ResampleParams p;
     p.x = in_dev;
