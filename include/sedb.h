@@ -105,7 +105,9 @@ int sedb_logmel_host_f32(sedb_ctx_t* ctx, const float* wave_host, long long n_cl
  * in: [n_clips, in_stride] float32 device, n_in valid samples per clip; out: [n_clips, out_stride] with
  * sedb_resample_num_samples(n_in, sr_in, sr_out) = ceil(n_in * sr_out / sr_in) samples per clip.  The
  * first call for a rate pair builds and uploads its filter table (allocates and synchronises: do it
- * outside graph capture).  Rates that reduce to more than 4096 : 4096 are refused. */
+ * outside graph capture).  Rates that reduce to more than 4096 : 4096 are refused.  Rate pairs with 64-256 phases
+ * (44.1 -> 48 kHz: 160) run as a tcgen05 GEMM against a Toeplitz view of the input, the others as a CUDA-core
+ * polyphase FIR; the environment variable SEDB_RESAMPLE_FIR forces the latter. */
 long long sedb_resample_num_samples(long long n_in, int sr_in, int sr_out);
 /* The filter table the converter uses for a rate pair, [taps][phases] float32 (host; no GPU needed): tap k of
  * phase p weighs x[i * Lo + k - width] in y[i * Ln + p].  out_host may be null to query the sizes. */

@@ -16,6 +16,10 @@ for i in range(0, y2.shape[1], 15840):
     y2[:, i:i + 15840] *= (1e-3, 0.5, 0.05, 1.0, 0.0, 0.2)[(i // 15840) % 6]
 lm2 = P.waveform_to_log_mel(torch.from_numpy(np.clip(y2, -1, 1)).cuda())
 lm3 = P.pcm16_to_log_mel(torch.from_numpy((np.clip(y2[:40], -1, 1) * 32767).astype(np.int16)).cuda())
+# sample-rate conversion: tensor-core path (160 phases, three tiles per clip) and the CUDA-core FIR (3 phases)
+from sed_b200.dataset import dataset_utils as DU
+rs1 = DU.resample(torch.from_numpy(y2[:3, :44100]).cuda(), 44100, 48000)
+rs2 = DU.resample(torch.from_numpy(y2[:3, :16000]).cuda(), 16000, 48000)
 m, _ = refmodels.seeded_cnn(refmodels.MAIN_CFG); m = m.cuda()
 p = m.logits(torch.randn(3, 1, 61, 64, device="cuda"))
 m5, _ = refmodels.seeded_m5(); m5 = m5.cuda()
